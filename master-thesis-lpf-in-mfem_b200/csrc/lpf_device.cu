@@ -1,0 +1,808 @@
+// Device context and C-ABI of the B200 hot path (include/lpf_b200.h, "Device context" section).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lpf_b200.h"
+#include "../host/lpf_common.hpp"
+#include "../host/lpf_host.hpp"
+#include "lpf_comm.hpp"
+#include "pa_kernels.cuh"
+#include "vec_kernels.cuh"
+
+#define CUDA_TRY(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t err__ = (call);                                                                 \
+        if (err__ != cudaSuccess) {                                                                 \
+            lpf::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" __FILE__ ":" + \
+                           std::to_string(__LINE__) + ")");                                         \
+            return LPF_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+#define LPF_TRY(call)                    \
+    do {                                 \
+        int rc__ = (call);               \
+        if (rc__ != LPF_OK) return rc__; \
+    } while (0)
+
+namespace {
+
+template <class T>
+int upload(T *&dst, const T *src, size_t n, size_t *bytes)
+{
+    dst = nullptr;
+    if (n == 0) return LPF_OK;
+    CUDA_TRY(cudaMalloc((void **)&dst, n * sizeof(T)));
+    if (src) CUDA_TRY(cudaMemcpy(dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    else CUDA_TRY(cudaMemset(dst, 0, n * sizeof(T)));
+    if (bytes) *bytes += n * sizeof(T);
+    return LPF_OK;
+}
+
+inline int vec_grid(int n, int sm_count)
+{
+    const int need = (n + 255) / 256;
+    return std::max(1, std::min(need, std::min(sm_count * 8, LPF_MAX_PARTIALS)));
+}
+
+}  // namespace
+
+struct lpf_ctx {
+    int dev = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int p = 0, D = 0, Q = 0, ne = 0, ndof = 0, ness = 0, nsurf = 0;
+    int nranks = 1, rank = 0;
+    long n_true_global = 0;
+    size_t bytes = 0;
+    long launches = 0;
+    bool setup_done = false, jacobi_done = false, rhs_done = false;
+    // options
+    int variant = 0;          // apply kernel variant (elements per CTA / prefetch), see apply_launch
+    int use_graph = 1, chunk = 16, skip_zero_apply = 1;
+    // geometry / maps
+    double *corners = nullptr, *jac = nullptr, *qd = nullptr;
+    int *gmap = nullptr, *gmap_c = nullptr, *ess = nullptr;
+    uint8_t *essmask = nullptr, *owned = nullptr, *surf_owned = nullptr;
+    // solver vectors
+    double *dinv = nullptr, *r = nullptr, *z = nullptr, *d = nullptr, *ad = nullptr, *X = nullptr, *Bv = nullptr, *tmp = nullptr;
+    double *den_slots = nullptr, *partials = nullptr;
+    PcgState *st = nullptr;
+    PcgState *st_host = nullptr;      // pinned
+    int *bad = nullptr;
+    // surface
+    int *surf2vol = nullptr, *surf_mult = nullptr, *sd_off = nullptr, *sd_elem = nullptr, *sd_node = nullptr;
+    double *surf_xy = nullptr, *cgen = nullptr, *cabs = nullptr, *wsum = nullptr;
+    double *rk_k = nullptr, *rk_y = nullptr, *rk_z = nullptr, *state_dev = nullptr;
+    double *state_pinned = nullptr;
+    RhsDev rhs{};
+    double rel_tol = 1e-12, abs_tol = 0.0;
+    int max_iter = 1000;
+    lpf_pcg_info last_info[4]{};
+    int n_last = 0;
+    // halo (multi-GPU)
+    lpf::Comm comm;
+    lpf::HaloPlan halo, shalo;
+    // host staging for *_host entry points
+    double *hx = nullptr, *hy = nullptr;
+    // CUDA graph of one PCG chunk
+    cudaGraphExec_t pcg_graph = nullptr;
+    int pcg_graph_chunk = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------------
+// apply kernel dispatch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+template <int P, int E, bool PF, bool EVEC, int MINB>
+int apply_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
+{
+    using C = ApplyCfg<P, E>;
+    auto kern = pa_apply_kernel<P, E, PF, EVEC, MINB>;
+    static bool attr_set[16] = {false};
+    if (!attr_set[c->dev & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        attr_set[c->dev & 15] = true;
+    }
+    const int grid = (c->ne + E - 1) / E;
+    if (grid == 0) return LPF_OK;
+    kern<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+// variant 0 = default for the order; other values pick alternative (E, prefetch) pairs for tuning
+template <bool EVEC>
+int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
+{
+    const int v = c->variant;
+    switch (c->p) {
+        case 1: return apply_launch_t<1, 16, true, EVEC, 1>(c, gmap, x, y, den, status);
+        case 2: return apply_launch_t<2, 16, true, EVEC, 1>(c, gmap, x, y, den, status);
+        case 3: return v == 1 ? apply_launch_t<3, 4, true, EVEC, 1>(c, gmap, x, y, den, status)
+                              : apply_launch_t<3, 8, true, EVEC, 1>(c, gmap, x, y, den, status);
+        case 4:
+            if (v == 1) return apply_launch_t<4, 8, true, EVEC, 1>(c, gmap, x, y, den, status);
+            if (v == 2) return apply_launch_t<4, 4, false, EVEC, 1>(c, gmap, x, y, den, status);
+            if (v == 3) return apply_launch_t<4, 2, true, EVEC, 1>(c, gmap, x, y, den, status);
+            if (v == 4) return apply_launch_t<4, 8, false, EVEC, 1>(c, gmap, x, y, den, status);
+            return apply_launch_t<4, 4, true, EVEC, 1>(c, gmap, x, y, den, status);
+        case 5: return v == 1 ? apply_launch_t<5, 2, true, EVEC, 1>(c, gmap, x, y, den, status)
+                              : apply_launch_t<5, 4, true, EVEC, 1>(c, gmap, x, y, den, status);
+        case 6: return v == 1 ? apply_launch_t<6, 2, true, EVEC, 1>(c, gmap, x, y, den, status)
+                              : apply_launch_t<6, 4, false, EVEC, 1>(c, gmap, x, y, den, status);
+        case 7: return apply_launch_t<7, 2, false, EVEC, 1>(c, gmap, x, y, den, status);
+        case 8: return apply_launch_t<8, 2, false, EVEC, 1>(c, gmap, x, y, den, status);
+        default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
+    }
+}
+
+int halo_sum(lpf_ctx *c, lpf::HaloPlan &h, double *v)
+{
+    if (c->nranks == 1 || h.n_nbr == 0) return LPF_OK;
+    if (!c->comm.ready()) { lpf::set_error("multi-rank context used before lpf_comm_init"); return LPF_ERR_STATE; }
+    const int ns = h.total;
+    halo_pack_kernel<<<(ns + 255) / 256, 256, 0, c->stream>>>(ns, h.send_dofs, v, h.sendbuf);
+    c->launches++;
+    LPF_TRY(c->comm.exchange(h, c->stream));
+    halo_unpack_kernel<<<(h.n_shared + 255) / 256, 256, 0, c->stream>>>(h.n_shared, h.shared, h.red_off, h.red_src, h.recvbuf, v);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+int upload_halo(lpf::HaloPlan &h, int n_nbr, const int *nbr_rank, const int *nbr_offset, const int *send, int n_shared,
+                const int *shared, const int *red_off, const int *red_src, size_t *bytes)
+{
+    h.n_nbr = n_nbr;
+    h.nbr_rank.assign(nbr_rank, nbr_rank + n_nbr);
+    h.nbr_offset.assign(nbr_offset, nbr_offset + n_nbr + 1);
+    h.total = n_nbr ? nbr_offset[n_nbr] : 0;
+    h.n_shared = n_shared;
+    if (h.total == 0) return LPF_OK;
+    LPF_TRY(upload(h.send_dofs, send, (size_t)h.total, bytes));
+    LPF_TRY(upload(h.shared, shared, (size_t)n_shared, bytes));
+    LPF_TRY(upload(h.red_off, red_off, (size_t)n_shared + 1, bytes));
+    LPF_TRY(upload(h.red_src, red_src, (size_t)red_off[n_shared], bytes));
+    LPF_TRY(upload(h.sendbuf, (const double *)nullptr, (size_t)h.total, bytes));
+    LPF_TRY(upload(h.recvbuf, (const double *)nullptr, (size_t)h.total, bytes));
+    return LPF_OK;
+}
+
+int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
+{
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { lpf::set_error("lpf_create: no such CUDA device"); return LPF_ERR_CUDA; }
+    CUDA_TRY(cudaSetDevice(device));
+    c->dev = device;
+    CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    c->p = d->order; c->D = d->order + 1; c->Q = d->order + 2;
+    c->ne = d->ne; c->ndof = d->ndof; c->ness = d->n_ess; c->nsurf = d->n_surf;
+    c->nranks = d->nranks > 0 ? d->nranks : 1; c->rank = d->rank;
+    c->n_true_global = d->n_true_global ? d->n_true_global : d->ndof;
+    const int D3 = c->D * c->D * c->D, Q3 = c->Q * c->Q * c->Q;
+
+    // basis tables -> constant memory (slot p)
+    {
+        lpf::Basis1D bs(c->p);
+        LpfBasisTab t;
+        std::memset(&t, 0, sizeof(t));
+        std::copy(bs.B.begin(), bs.B.end(), t.B);
+        std::copy(bs.G.begin(), bs.G.end(), t.G);
+        std::copy(bs.Dhat.begin(), bs.Dhat.end(), t.Dhat);
+        std::copy(bs.nodes.begin(), bs.nodes.end(), t.nodes);
+        std::copy(bs.qpts.begin(), bs.qpts.end(), t.qpts);
+        std::copy(bs.qwts.begin(), bs.qwts.end(), t.qwts);
+        CUDA_TRY(cudaMemcpyToSymbol(c_tab, &t, sizeof(t), sizeof(LpfBasisTab) * c->p));
+    }
+    if (d->corners) LPF_TRY(upload(c->corners, d->corners, (size_t)c->ne * 24, &c->bytes));
+    if (d->jac) LPF_TRY(upload(c->jac, d->jac, (size_t)c->ne * Q3 * 9, &c->bytes));
+    LPF_TRY(upload(c->gmap, d->gather, (size_t)c->ne * D3, &c->bytes));
+    {   // constrained map: essential dofs encoded as ~dof (gather reads 0, scatter skips)
+        std::vector<uint8_t> em((size_t)c->ndof, 0);
+        for (int i = 0; i < c->ness; i++) {
+            if (d->ess[i] < 0 || d->ess[i] >= c->ndof) { lpf::set_error("lpf_create: essential dof out of range"); return LPF_ERR_ARG; }
+            em[d->ess[i]] = 1;
+        }
+        std::vector<int> gc((size_t)c->ne * D3);
+        for (size_t i = 0; i < gc.size(); i++) {
+            const int g = d->gather[i];
+            if (g < 0 || g >= c->ndof) { lpf::set_error("lpf_create: gather index out of range"); return LPF_ERR_ARG; }
+            gc[i] = em[g] ? ~g : g;
+        }
+        LPF_TRY(upload(c->gmap_c, gc.data(), gc.size(), &c->bytes));
+        LPF_TRY(upload(c->essmask, em.data(), em.size(), &c->bytes));
+        LPF_TRY(upload(c->ess, d->ess, (size_t)c->ness, &c->bytes));
+    }
+    LPF_TRY(upload(c->qd, (const double *)nullptr, (size_t)c->ne * 6 * Q3, &c->bytes));
+    const size_t n = (size_t)c->ndof;
+    LPF_TRY(upload(c->dinv, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->r, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->z, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->d, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->ad, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->X, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->Bv, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->tmp, (const double *)nullptr, n, &c->bytes));
+    LPF_TRY(upload(c->den_slots, (const double *)nullptr, LPF_DEN_SLOTS, &c->bytes));
+    LPF_TRY(upload(c->partials, (const double *)nullptr, LPF_MAX_PARTIALS, &c->bytes));
+    LPF_TRY(upload(c->st, (const PcgState *)nullptr, 1, &c->bytes));
+    LPF_TRY(upload(c->bad, (const int *)nullptr, 1, &c->bytes));
+    CUDA_TRY(cudaMallocHost((void **)&c->st_host, sizeof(PcgState)));
+    if (c->nranks > 1) {
+        if (!d->owned) { lpf::set_error("lpf_create: multi-rank descriptor without ownership mask"); return LPF_ERR_ARG; }
+        LPF_TRY(upload(c->owned, d->owned, n, &c->bytes));
+        LPF_TRY(upload_halo(c->halo, d->n_nbr, d->nbr_rank, d->nbr_offset, d->send_dofs, d->n_shared, d->shared_dofs,
+                            d->red_off, d->red_src, &c->bytes));
+        LPF_TRY(upload_halo(c->shalo, d->s_n_nbr, d->s_nbr_rank, d->s_nbr_offset, d->s_send, d->s_n_shared, d->s_shared,
+                            d->s_red_off, d->s_red_src, &c->bytes));
+    }
+    // surface tables
+    if (c->nsurf > 0) {
+        const size_t ns = (size_t)c->nsurf;
+        LPF_TRY(upload(c->surf2vol, d->surf2vol, ns, &c->bytes));
+        LPF_TRY(upload(c->surf_xy, d->surf_xy, 2 * ns, &c->bytes));
+        std::vector<int> vol2surf((size_t)c->ndof, -1);
+        for (int s = 0; s < c->nsurf; s++) vol2surf[d->surf2vol[s]] = s;
+        // per surface dof: the (element, local node) pairs contributing to GetDerivative, element order
+        std::vector<int> cnt(ns + 1, 0);
+        std::vector<int> elems;
+        if (d->surf_elems) elems.assign(d->surf_elems, d->surf_elems + d->n_surf_elems);
+        else { elems.resize(c->ne); for (int e = 0; e < c->ne; e++) elems[e] = e; }
+        for (int e : elems)
+            for (int k = 0; k < D3; k++) { const int s = vol2surf[d->gather[(size_t)e * D3 + k]]; if (s >= 0) cnt[s + 1]++; }
+        for (size_t s = 0; s < ns; s++) cnt[s + 1] += cnt[s];
+        std::vector<int> se(cnt[ns]), sn(cnt[ns]), pos(cnt.begin(), cnt.end() - 1);
+        for (int e : elems)
+            for (int k = 0; k < D3; k++) {
+                const int s = vol2surf[d->gather[(size_t)e * D3 + k]];
+                if (s >= 0) { se[pos[s]] = e; sn[pos[s]] = k; pos[s]++; }
+            }
+        std::vector<int> mult(ns);
+        for (size_t s = 0; s < ns; s++) mult[s] = d->surf_mult ? d->surf_mult[s] : cnt[s + 1] - cnt[s];
+        LPF_TRY(upload(c->sd_off, cnt.data(), ns + 1, &c->bytes));
+        LPF_TRY(upload(c->sd_elem, se.data(), se.size(), &c->bytes));
+        LPF_TRY(upload(c->sd_node, sn.data(), sn.size(), &c->bytes));
+        LPF_TRY(upload(c->surf_mult, mult.data(), ns, &c->bytes));
+        LPF_TRY(upload(c->wsum, (const double *)nullptr, ns, &c->bytes));
+        LPF_TRY(upload(c->cgen, (const double *)nullptr, ns, &c->bytes));
+        LPF_TRY(upload(c->cabs, (const double *)nullptr, ns, &c->bytes));
+        LPF_TRY(upload(c->rk_k, (const double *)nullptr, 2 * ns, &c->bytes));
+        LPF_TRY(upload(c->rk_y, (const double *)nullptr, 2 * ns, &c->bytes));
+        LPF_TRY(upload(c->rk_z, (const double *)nullptr, 2 * ns, &c->bytes));
+        LPF_TRY(upload(c->state_dev, (const double *)nullptr, 2 * ns, &c->bytes));
+        CUDA_TRY(cudaMallocHost((void **)&c->state_pinned, 2 * ns * sizeof(double)));
+        if (c->nranks > 1 && d->surf_owned) LPF_TRY(upload(c->surf_owned, d->surf_owned, ns, &c->bytes));
+    }
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    return LPF_OK;
+}
+
+void free_halo(lpf::HaloPlan &h)
+{
+    cudaFree(h.send_dofs); cudaFree(h.shared); cudaFree(h.red_off); cudaFree(h.red_src); cudaFree(h.sendbuf); cudaFree(h.recvbuf);
+}
+
+}  // namespace
+
+extern "C" {
+
+lpf_ctx *lpf_create(const lpf_space_desc *desc, int device, void *stream)
+{
+    if (!desc || !desc->gather || (!desc->corners && !desc->jac) || desc->ne < 0 || desc->ndof <= 0) {
+        lpf::set_error("lpf_create: incomplete descriptor");
+        return nullptr;
+    }
+    if (desc->order < 1 || desc->order > LPF_MAXP) { lpf::set_error("lpf_create: order must be in 1..8"); return nullptr; }
+    if (desc->n_ess > 0 && !desc->ess) { lpf::set_error("lpf_create: n_ess > 0 but ess == NULL"); return nullptr; }
+    auto *c = new lpf_ctx;
+    if (create_impl(c, desc, device, stream) != LPF_OK) { lpf_destroy(c); return nullptr; }
+    return c;
+}
+
+void lpf_destroy(lpf_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->dev);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->pcg_graph) cudaGraphExecDestroy(c->pcg_graph);
+    c->comm.destroy();
+    void *ptrs[] = {c->corners, c->jac, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
+                    c->z, c->d, c->ad, c->X, c->Bv, c->tmp, c->den_slots, c->partials, c->st, c->bad, c->surf2vol,
+                    c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->wsum, c->rk_k,
+                    c->rk_y, c->rk_z, c->state_dev};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    free_halo(c->halo); free_halo(c->shalo);
+    if (c->st_host) cudaFreeHost(c->st_host);
+    if (c->state_pinned) cudaFreeHost(c->state_pinned);
+    if (c->hx) cudaFreeHost(c->hx);
+    if (c->hy) cudaFreeHost(c->hy);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void *lpf_stream(lpf_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int lpf_sync(lpf_ctx *c)
+{
+    if (!c) { lpf::set_error("null context"); return LPF_ERR_ARG; }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LPF_OK;
+}
+int lpf_ndof(const lpf_ctx *c) { return c ? c->ndof : LPF_ERR_ARG; }
+int lpf_nsurf(const lpf_ctx *c) { return c ? c->nsurf : LPF_ERR_ARG; }
+long lpf_launch_count(lpf_ctx *c) { return c ? c->launches : 0; }
+size_t lpf_device_bytes(const lpf_ctx *c) { return c ? c->bytes : 0; }
+
+int lpf_set_option(lpf_ctx *c, const char *name, long value)
+{
+    if (!c || !name) { lpf::set_error("lpf_set_option: null argument"); return LPF_ERR_ARG; }
+    const std::string k(name);
+    if (k == "apply_variant") c->variant = (int)value;
+    else if (k == "use_graph") c->use_graph = (int)value;
+    else if (k == "pcg_chunk") { if (value < 1) { lpf::set_error("pcg_chunk must be >= 1"); return LPF_ERR_ARG; } c->chunk = (int)value; }
+    else if (k == "skip_zero_apply") c->skip_zero_apply = (int)value;
+    else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
+    if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
+    return LPF_OK;
+}
+
+int lpf_comm_unique_id(void *id128) { return lpf::Comm::unique_id(id128); }
+int lpf_comm_init(lpf_ctx *c, const void *id128)
+{
+    if (!c || !id128) { lpf::set_error("lpf_comm_init: null argument"); return LPF_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(c->dev));
+    return c->comm.init(id128, c->nranks, c->rank);
+}
+
+// ---- a1 -------------------------------------------------------------------------------------------
+int lpf_pa_setup(lpf_ctx *c)
+{
+    if (!c) { lpf::set_error("null context"); return LPF_ERR_ARG; }
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const size_t nq = (size_t)c->ne * c->Q * c->Q * c->Q;
+    if (nq) {
+        pa_setup_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->p, c->ne, c->corners, c->jac, c->qd);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    c->setup_done = true;
+    return LPF_OK;
+}
+
+int lpf_pa_qdata(lpf_ctx *c, double *out)
+{
+    if (!c || !out) { lpf::set_error("lpf_pa_qdata: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_pa_qdata before lpf_pa_setup"); return LPF_ERR_STATE; }
+    const size_t nq = (size_t)c->ne * c->Q * c->Q * c->Q;
+    if (nq) {
+        pa_qdata_export_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->p, c->ne, c->qd, out);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LPF_OK;
+}
+
+// ---- a8 -------------------------------------------------------------------------------------------
+int lpf_pa_apply_E(lpf_ctx *c, const double *xE, double *yE)
+{
+    if (!c || !xE || !yE) { lpf::set_error("lpf_pa_apply_E: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_pa_apply_E before lpf_pa_setup"); return LPF_ERR_STATE; }
+    return apply_launch<true>(c, nullptr, xE, yE, nullptr, nullptr);
+}
+
+int lpf_apply_L(lpf_ctx *c, const double *x, double *y)
+{
+    if (!c || !x || !y) { lpf::set_error("lpf_apply_L: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_apply_L before lpf_pa_setup"); return LPF_ERR_STATE; }
+    CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
+    return apply_launch<false>(c, c->gmap, x, y, nullptr, nullptr);
+}
+
+int lpf_apply_T(lpf_ctx *c, const double *x, double *y)
+{
+    if (!c || !x || !y) { lpf::set_error("lpf_apply_T: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_apply_T before lpf_pa_setup"); return LPF_ERR_STATE; }
+    CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
+    LPF_TRY(apply_launch<false>(c, c->gmap_c, x, y, nullptr, nullptr));
+    LPF_TRY(halo_sum(c, c->halo, y));
+    if (c->ness) {
+        copy_at_kernel<<<(c->ness + 255) / 256, 256, 0, c->stream>>>(c->ness, c->ess, x, y);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LPF_OK;
+}
+
+int lpf_apply_T_host(lpf_ctx *c, const double *xh, double *yh)
+{
+    if (!c || !xh || !yh) { lpf::set_error("lpf_apply_T_host: null argument"); return LPF_ERR_ARG; }
+    const size_t nb = sizeof(double) * c->ndof;
+    CUDA_TRY(cudaMemcpyAsync(c->X, xh, nb, cudaMemcpyHostToDevice, c->stream));
+    LPF_TRY(lpf_apply_T(c, c->X, c->tmp));
+    CUDA_TRY(cudaMemcpyAsync(yh, c->tmp, nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LPF_OK;
+}
+
+// ---- a2 -------------------------------------------------------------------------------------------
+int lpf_diag(lpf_ctx *c, double *diag)
+{
+    if (!c || !diag) { lpf::set_error("lpf_diag: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_diag before lpf_pa_setup"); return LPF_ERR_STATE; }
+    CUDA_TRY(cudaMemsetAsync(diag, 0, sizeof(double) * c->ndof, c->stream));
+    const size_t n = (size_t)c->ne * c->D * c->D * c->D;
+    if (n) {
+        pa_diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->p, c->ne, c->qd, c->gmap, diag);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return halo_sum(c, c->halo, diag);
+}
+
+int lpf_jacobi_setup(lpf_ctx *c)
+{
+    if (!c) { lpf::set_error("null context"); return LPF_ERR_ARG; }
+    LPF_TRY(lpf_diag(c, c->tmp));
+    CUDA_TRY(cudaMemsetAsync(c->bad, 0, sizeof(int), c->stream));
+    dinv_kernel<<<vec_grid(c->ndof, c->sm_count), 256, 0, c->stream>>>(c->ndof, c->tmp, c->essmask, c->dinv, c->bad);
+    c->launches++;
+    int bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, c->bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (bad) { lpf::set_error("lpf_jacobi_setup: non-positive diagonal entry (MFEM_VERIFY in OperatorJacobiSmoother)"); return LPF_ERR_STATE; }
+    c->jacobi_done = true;
+    return LPF_OK;
+}
+
+int lpf_jacobi_dinv(lpf_ctx *c, double *out)
+{
+    if (!c || !out) { lpf::set_error("lpf_jacobi_dinv: null argument"); return LPF_ERR_ARG; }
+    if (!c->jacobi_done) { lpf::set_error("lpf_jacobi_dinv before lpf_jacobi_setup"); return LPF_ERR_STATE; }
+    CUDA_TRY(cudaMemcpyAsync(out, c->dinv, sizeof(double) * c->ndof, cudaMemcpyDeviceToDevice, c->stream));
+    return LPF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// PCG
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// one CG iteration body: update (+ dot), direction, apply (+ den); all skip themselves once status != 0
+int pcg_iteration(lpf_ctx *c)
+{
+    const int n = c->ndof, g = vec_grid(n, c->sm_count);
+    const bool multi = c->nranks > 1;
+    if (multi) {
+        pcg_update_kernel<true><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->den_slots, c->partials);
+        c->launches++;
+        LPF_TRY(c->comm.allreduce_sum(&c->st->red[0], 1, c->stream));
+        pcg_fin_beta_kernel<<<1, 1, 0, c->stream>>>(c->st);
+        c->launches++;
+    } else {
+        pcg_update_kernel<false><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, nullptr, c->st, c->den_slots, c->partials);
+        c->launches++;
+    }
+    pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
+    c->launches++;
+    LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+    if (multi) {
+        LPF_TRY(halo_sum(c, c->halo, c->ad));
+        pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
+        c->launches++;
+        LPF_TRY(c->comm.allreduce_sum(&c->st->red[1], 1, c->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+int pcg_chunk(lpf_ctx *c)
+{
+    if (!c->use_graph) {
+        for (int i = 0; i < c->chunk; i++) LPF_TRY(pcg_iteration(c));
+        return LPF_OK;
+    }
+    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk) {
+        if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        const long l0 = c->launches;
+        CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = LPF_OK;
+        for (int i = 0; i < c->chunk && rc == LPF_OK; i++) rc = pcg_iteration(c);
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        c->launches = l0;
+        if (rc != LPF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        CUDA_TRY(ce);
+        CUDA_TRY(cudaGraphInstantiate(&c->pcg_graph, graph, 0));
+        cudaGraphDestroy(graph);
+        c->pcg_graph_chunk = c->chunk;
+    }
+    CUDA_TRY(cudaGraphLaunch(c->pcg_graph, c->stream));
+    c->launches += (long)c->chunk * (c->nranks > 1 ? 7 : 3);
+    return LPF_OK;
+}
+
+// Solve A_c X = B with X (ctx-owned c->X) as initial guess, B in c->Bv.  zero_guess_interior: the caller
+// guarantees X is zero off the essential dofs, so A_c X == [0 ; X_ess] exactly and the initial-residual
+// apply of CGSolver::Mult can be skipped without changing a single bit of r.
+int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_guess_interior, lpf_pcg_info *info)
+{
+    const int n = c->ndof, g = vec_grid(n, c->sm_count);
+    const bool multi = c->nranks > 1;
+    int applies = 0;
+    pcg_reset_kernel<<<1, 256, 0, c->stream>>>(c->st, c->den_slots, rel_tol, abs_tol, max_iter);
+    c->launches++;
+    const double *t = nullptr;
+    if (!(zero_guess_interior && c->skip_zero_apply)) {
+        LPF_TRY(lpf_apply_T(c, c->X, c->tmp));
+        applies++;
+        t = c->tmp;
+    } else if (c->ness) {
+        // r = B - [0 ; X_ess]: B_ess == X_ess by construction, so r_ess = 0: do it through tmp = [0 ; X_ess]
+        CUDA_TRY(cudaMemsetAsync(c->tmp, 0, sizeof(double) * n, c->stream));
+        copy_at_kernel<<<(c->ness + 255) / 256, 256, 0, c->stream>>>(c->ness, c->ess, c->X, c->tmp);
+        c->launches++;
+        t = c->tmp;
+    }
+    if (multi) {
+        pcg_init_kernel<true><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials);
+        c->launches++;
+        LPF_TRY(c->comm.allreduce_sum(&c->st->red[0], 1, c->stream));
+        pcg_fin_nom_kernel<<<1, 1, 0, c->stream>>>(c->st);
+        c->launches++;
+    } else {
+        pcg_init_kernel<false><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, nullptr, c->r, c->z, c->d, c->ad, c->st, c->partials);
+        c->launches++;
+    }
+    LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+    if (multi) {
+        LPF_TRY(halo_sum(c, c->halo, c->ad));
+        pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
+        c->launches++;
+        LPF_TRY(c->comm.allreduce_sum(&c->st->red[1], 1, c->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    // iterate in chunks; the only host round trip is the status poll after each chunk
+    for (;;) {
+        CUDA_TRY(cudaMemcpyAsync(c->st_host, c->st, sizeof(PcgState), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (c->st_host->status != PCG_RUNNING) break;
+        LPF_TRY(pcg_chunk(c));
+    }
+    const PcgState &s = *c->st_host;
+    // applies: 1 for the first A d (if the solve got that far) + one per completed direction update
+    if (!(s.status == PCG_CONVERGED && s.final_iter == 0) && s.status != PCG_NOT_PD) applies += 1;
+    applies += std::max(0, s.iter - 1) - (s.status == PCG_MAXITER ? 1 : 0);
+    if (info) {
+        info->iterations = s.final_iter;
+        info->converged = s.status == PCG_CONVERGED;
+        info->final_norm = std::sqrt(std::max(s.betanom, 0.0));
+        info->initial_norm = std::sqrt(std::max(s.nom0, 0.0));
+        info->applies = applies;
+    }
+    return LPF_OK;
+}
+
+int solve_from_X(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, lpf_pcg_info *info)
+{
+    // FormLinearSystem: c->X holds [0 ; x_ess].  B = -A X (unconstrained), B[ess] = X[ess]   (EliminateRHS)
+    const int n = c->ndof;
+    CUDA_TRY(cudaMemsetAsync(c->tmp, 0, sizeof(double) * n, c->stream));
+    LPF_TRY(apply_launch<false>(c, c->gmap, c->X, c->tmp, nullptr, nullptr));
+    LPF_TRY(halo_sum(c, c->halo, c->tmp));
+    negate_kernel<<<vec_grid(n, c->sm_count), 256, 0, c->stream>>>(n, c->tmp, c->Bv);
+    c->launches++;
+    if (c->ness) {
+        copy_at_kernel<<<(c->ness + 255) / 256, 256, 0, c->stream>>>(c->ness, c->ess, c->X, c->Bv);
+        c->launches++;
+    }
+    LPF_TRY(pcg_run(c, rel_tol, abs_tol, max_iter, true, info));
+    if (info) info->applies += 1;
+    return LPF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lpf_pcg(lpf_ctx *c, const double *B, double *X, double rel_tol, double abs_tol, int max_iter, lpf_pcg_info *info)
+{
+    if (!c || !B || !X) { lpf::set_error("lpf_pcg: null argument"); return LPF_ERR_ARG; }
+    if (!c->jacobi_done) { lpf::set_error("lpf_pcg before lpf_jacobi_setup"); return LPF_ERR_STATE; }
+    if (max_iter < 0) { lpf::set_error("lpf_pcg: negative max_iter"); return LPF_ERR_ARG; }
+    const size_t nb = sizeof(double) * c->ndof;
+    CUDA_TRY(cudaMemcpyAsync(c->X, X, nb, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->Bv, B, nb, cudaMemcpyDeviceToDevice, c->stream));
+    LPF_TRY(pcg_run(c, rel_tol, abs_tol, max_iter, false, info));
+    CUDA_TRY(cudaMemcpyAsync(X, c->X, nb, cudaMemcpyDeviceToDevice, c->stream));
+    return LPF_OK;
+}
+
+int lpf_laplace_solve(lpf_ctx *c, double *phi, double rel_tol, double abs_tol, int max_iter, lpf_pcg_info *info)
+{
+    if (!c || !phi) { lpf::set_error("lpf_laplace_solve: null argument"); return LPF_ERR_ARG; }
+    if (!c->jacobi_done) { lpf::set_error("lpf_laplace_solve before lpf_jacobi_setup"); return LPF_ERR_STATE; }
+    const size_t nb = sizeof(double) * c->ndof;
+    CUDA_TRY(cudaMemsetAsync(c->X, 0, nb, c->stream));
+    if (c->ness) {
+        copy_at_kernel<<<(c->ness + 255) / 256, 256, 0, c->stream>>>(c->ness, c->ess, phi, c->X);
+        c->launches++;
+    }
+    LPF_TRY(solve_from_X(c, rel_tol, abs_tol, max_iter, info));
+    CUDA_TRY(cudaMemcpyAsync(phi, c->X, nb, cudaMemcpyDeviceToDevice, c->stream));
+    return LPF_OK;
+}
+
+int lpf_surface_dz(lpf_ctx *c, const double *phi, double *wt)
+{
+    if (!c || !phi || !wt) { lpf::set_error("lpf_surface_dz: null argument"); return LPF_ERR_ARG; }
+    if (c->nsurf == 0) return LPF_OK;
+    const int ns = c->nsurf;
+    surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, phi, c->wsum);
+    c->launches++;
+    LPF_TRY(halo_sum(c, c->shalo, c->wsum));
+    surface_div_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(ns, c->surf_mult, c->wsum, wt);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+int lpf_rhs_setup(lpf_ctx *c, const lpf_rhs_params *p, const double *cgen, const double *cabs)
+{
+    if (!c || !p) { lpf::set_error("lpf_rhs_setup: null argument"); return LPF_ERR_ARG; }
+    if (!c->corners) { lpf::set_error("lpf_rhs_setup: surface derivative needs the corner geometry"); return LPF_ERR_STATE; }
+    if (p->use_relaxation && (!cgen || !cabs || !(p->tau > 0.0))) { lpf::set_error("lpf_rhs_setup: relaxation needs cgen, cabs and tau > 0"); return LPF_ERR_ARG; }
+    c->rhs.g = p->g; c->rhs.H = p->H; c->rhs.omega = p->omega; c->rhs.k = p->k; c->rhs.kx = p->kx_dir; c->rhs.ky = p->ky_dir;
+    c->rhs.cwave = p->cwave; c->rhs.coth_kh = std::cosh(p->kh) / std::sinh(p->kh); c->rhs.T = p->T;
+    c->rhs.inv_tau = p->use_relaxation ? 1.0 / p->tau : 0.0; c->rhs.n_ramp = p->n_ramp; c->rhs.relax = p->use_relaxation;
+    c->rel_tol = p->rel_tol; c->abs_tol = p->abs_tol; c->max_iter = p->max_iter;
+    if (p->use_relaxation && c->nsurf) {
+        CUDA_TRY(cudaMemcpyAsync(c->cgen, cgen, sizeof(double) * c->nsurf, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->cabs, cabs, sizeof(double) * c->nsurf, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    c->rhs_done = true;
+    return LPF_OK;
+}
+
+static int rhs_impl(lpf_ctx *c, double t, const double *state, double *dstate, lpf_pcg_info *info)
+{
+    const int ns = c->nsurf;
+    // eta_stage/phi_fs_stage -> phi on the free surface, interior zero (Transfer + FormLinearSystem)
+    CUDA_TRY(cudaMemsetAsync(c->X, 0, sizeof(double) * c->ndof, c->stream));
+    if (ns) {
+        scatter_kernel<<<(ns + 255) / 256, 256, 0, c->stream>>>(ns, c->surf2vol, state + ns, c->X);
+        c->launches++;
+    }
+    LPF_TRY(solve_from_X(c, c->rel_tol, c->abs_tol, c->max_iter, info));
+    if (ns) {
+        surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, c->X, c->wsum);
+        c->launches++;
+        LPF_TRY(halo_sum(c, c->shalo, c->wsum));
+        surface_rhs_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(ns, c->rhs, t, c->surf_mult, c->wsum, state, c->surf_xy, c->cgen, c->cabs, dstate);
+        c->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+int lpf_rhs(lpf_ctx *c, double t, const double *state, double *dstate)
+{
+    if (!c || !state || !dstate) { lpf::set_error("lpf_rhs: null argument"); return LPF_ERR_ARG; }
+    if (!c->rhs_done || !c->jacobi_done) { lpf::set_error("lpf_rhs before lpf_rhs_setup / lpf_jacobi_setup"); return LPF_ERR_STATE; }
+    c->n_last = 1;
+    return rhs_impl(c, t, state, dstate, &c->last_info[0]);
+}
+
+int lpf_rk4_step(lpf_ctx *c, double *x, double *t, double dt)
+{
+    if (!c || !x || !t) { lpf::set_error("lpf_rk4_step: null argument"); return LPF_ERR_ARG; }
+    if (!c->rhs_done || !c->jacobi_done) { lpf::set_error("lpf_rk4_step before lpf_rhs_setup / lpf_jacobi_setup"); return LPF_ERR_STATE; }
+    const int n2 = 2 * c->nsurf;
+    const int g = std::max(1, (n2 + 255) / 256);
+    const double ts[4] = {*t, *t + dt / 2, *t + dt / 2, *t + dt};
+    c->n_last = 4;
+    for (int s = 0; s < 4; s++) {
+        LPF_TRY(rhs_impl(c, ts[s], s == 0 ? x : c->rk_y, c->rk_k, &c->last_info[s]));
+        if (n2) {
+            rk4_stage_kernel<<<g, 256, 0, c->stream>>>(n2, s, dt, x, c->rk_k, c->rk_y, c->rk_z);
+            c->launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    *t += dt;
+    return LPF_OK;
+}
+
+int lpf_rk4_step_host(lpf_ctx *c, double *xh, double *t, double dt)
+{
+    if (!c || !xh || !t) { lpf::set_error("lpf_rk4_step_host: null argument"); return LPF_ERR_ARG; }
+    const size_t nb = sizeof(double) * 2 * c->nsurf;
+    if (nb) {
+        std::memcpy(c->state_pinned, xh, nb);
+        CUDA_TRY(cudaMemcpyAsync(c->state_dev, c->state_pinned, nb, cudaMemcpyHostToDevice, c->stream));
+    }
+    LPF_TRY(lpf_rk4_step(c, c->state_dev, t, dt));
+    if (nb) {
+        CUDA_TRY(cudaMemcpyAsync(c->state_pinned, c->state_dev, nb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        std::memcpy(xh, c->state_pinned, nb);
+    }
+    return LPF_OK;
+}
+
+int lpf_last_solve_info(lpf_ctx *c, lpf_pcg_info info[4], int *nsolves)
+{
+    if (!c || !info || !nsolves) { lpf::set_error("lpf_last_solve_info: null argument"); return LPF_ERR_ARG; }
+    for (int i = 0; i < c->n_last; i++) info[i] = c->last_info[i];
+    *nsolves = c->n_last;
+    return LPF_OK;
+}
+
+const double *lpf_phi_dev(lpf_ctx *c) { return c ? c->X : nullptr; }
+
+int lpf_time_apply(lpf_ctx *c, const double *x, double *y, int reps, float *ms_total, float *ms_kernel, long *n_launches)
+{
+    if (!c || !x || !y || reps < 1) { lpf::set_error("lpf_time_apply: bad argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_time_apply before lpf_pa_setup"); return LPF_ERR_STATE; }
+    const long l0 = c->launches;
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; i++) LPF_TRY(lpf_apply_T(c, x, y));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    if (ms_total) CUDA_TRY(cudaEventElapsedTime(ms_total, c->ev0, c->ev1));
+    if (n_launches) *n_launches = c->launches - l0;
+    if (ms_kernel) {
+        CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+        for (int i = 0; i < reps; i++) LPF_TRY(apply_launch<false>(c, c->gmap_c, x, y, nullptr, nullptr));
+        CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(c->ev1));
+        CUDA_TRY(cudaEventElapsedTime(ms_kernel, c->ev0, c->ev1));
+    }
+    return LPF_OK;
+}
+
+void *lpf_dev_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 8);
+    if (e != cudaSuccess) { lpf::set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+int lpf_dev_free(void *p) { CUDA_TRY(cudaFree(p)); return LPF_OK; }
+int lpf_memcpy_h2d(void *d, const void *s, size_t n) { CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyHostToDevice)); return LPF_OK; }
+int lpf_memcpy_d2h(void *d, const void *s, size_t n) { CUDA_TRY(cudaMemcpy(d, s, n, cudaMemcpyDeviceToHost)); return LPF_OK; }
+int lpf_memset_dev(void *d, int v, size_t n) { CUDA_TRY(cudaMemset(d, v, n)); return LPF_OK; }
+void *lpf_host_alloc_pinned(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 8);
+    if (e != cudaSuccess) { lpf::set_error(std::string("cudaMallocHost: ") + cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+int lpf_host_free_pinned(void *p) { CUDA_TRY(cudaFreeHost(p)); return LPF_OK; }
+int lpf_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,9 @@
+// Shared between the host mini-FEM layer and the device layer.
+#pragma once
+#include <string>
+
+#define LPF_MAX_ORDER 8
+
+namespace lpf {
+void set_error(const std::string &s);
+}

@@ -1,0 +1,758 @@
+// Host-side mini-FEM layer (see lpf_host.hpp for the reference call sites each piece stands in for).
+#include "lpf_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <numeric>
+#include <sstream>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace lpf {
+
+// ------------------------------------------------------------------------------------------------
+// 1-D basis tables
+// ------------------------------------------------------------------------------------------------
+static void legendre(int n, double x, double &p, double &dp)
+{
+    double p0 = 1.0, p1 = x;
+    if (n == 0) { p = 1.0; dp = 0.0; return; }
+    for (int k = 2; k <= n; k++) {
+        const double pk = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+        p0 = p1; p1 = pk;
+    }
+    p = p1;
+    dp = n * (x * p1 - p0) / (x * x - 1.0);
+}
+
+static std::vector<double> gll_points(int p)
+{
+    std::vector<double> x(p + 1);
+    if (p == 1) { x[0] = 0.0; x[1] = 1.0; return x; }
+    x[0] = -1.0; x[p] = 1.0;
+    for (int i = 1; i < p; i++) {
+        double xi = -std::cos(M_PI * i / p);
+        for (int it = 0; it < 100; it++) {
+            double pn, dpn;
+            legendre(p, xi, pn, dpn);
+            const double d2 = (2.0 * xi * dpn - p * (p + 1.0) * pn) / (1.0 - xi * xi);
+            const double dx = dpn / d2;
+            xi -= dx;
+            if (std::fabs(dx) < 1e-16) break;
+        }
+        x[i] = xi;
+    }
+    for (auto &v : x) v = 0.5 * (v + 1.0);
+    for (int i = 0; i <= p / 2; i++) {           // enforce exact symmetry about 1/2
+        const double a = 0.5 * (x[i] + (1.0 - x[p - i]));
+        x[i] = a; x[p - i] = 1.0 - a;
+    }
+    if (p % 2 == 0) x[p / 2] = 0.5;
+    return x;
+}
+
+static void gauss_legendre(int n, std::vector<double> &x, std::vector<double> &w)
+{
+    x.resize(n); w.resize(n);
+    for (int i = 0; i < n; i++) {
+        double xi = -std::cos((2.0 * (i + 1) - 1.0) * M_PI / (2.0 * n));
+        double pn, dpn;
+        for (int it = 0; it < 100; it++) {
+            legendre(n, xi, pn, dpn);
+            const double dx = pn / dpn;
+            xi -= dx;
+            if (std::fabs(dx) < 1e-16) break;
+        }
+        legendre(n, xi, pn, dpn);
+        x[i] = 0.5 * (xi + 1.0);
+        w[i] = 1.0 / ((1.0 - xi * xi) * dpn * dpn);
+    }
+    for (int i = 0; i < n / 2; i++) {
+        const double a = 0.5 * (x[i] + (1.0 - x[n - 1 - i]));
+        x[i] = a; x[n - 1 - i] = 1.0 - a;
+        const double b = 0.5 * (w[i] + w[n - 1 - i]);
+        w[i] = b; w[n - 1 - i] = b;
+    }
+    if (n % 2) x[n / 2] = 0.5;
+}
+
+static void lagrange(const std::vector<double> &nodes, double x, double *b, double *g)
+{
+    const int n = (int)nodes.size();
+    for (int d = 0; d < n; d++) {
+        double denom = 1.0, val = 1.0, der = 0.0;
+        for (int m = 0; m < n; m++) if (m != d) { denom *= nodes[d] - nodes[m]; val *= x - nodes[m]; }
+        for (int a = 0; a < n; a++) {
+            if (a == d) continue;
+            double t = 1.0;
+            for (int m = 0; m < n; m++) if (m != d && m != a) t *= x - nodes[m];
+            der += t;
+        }
+        b[d] = val / denom;
+        g[d] = der / denom;
+    }
+}
+
+Basis1D::Basis1D(int order) : p(order), D(order + 1), Q(order + 2)
+{
+    nodes = gll_points(p);
+    gauss_legendre(Q, qpts, qwts);
+    B.resize((size_t)Q * D); G.resize((size_t)Q * D); Dhat.resize((size_t)D * D);
+    for (int q = 0; q < Q; q++) lagrange(nodes, qpts[q], &B[(size_t)q * D], &G[(size_t)q * D]);
+    std::vector<double> tmp(D);
+    for (int a = 0; a < D; a++) lagrange(nodes, nodes[a], tmp.data(), &Dhat[(size_t)a * D]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Mesh
+// ------------------------------------------------------------------------------------------------
+static std::vector<std::string> tokenize_skip_comments(const std::string &path)
+{
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot open mesh file: " + path);
+    std::vector<std::string> tok;
+    std::string line;
+    while (std::getline(in, line)) {
+        size_t s = line.find_first_not_of(" \t\r");
+        if (s == std::string::npos || line[s] == '#') continue;
+        std::istringstream ls(line);
+        std::string t;
+        while (ls >> t) tok.push_back(t);
+    }
+    return tok;
+}
+
+static void corners_from_vertices(Mesh &m, const std::vector<double> &xyz)
+{
+    const int ne = m.ne();
+    m.corners.resize((size_t)ne * 24);
+    for (int e = 0; e < ne; e++)
+        for (int c = 0; c < 8; c++) {
+            const int v = m.elems[(size_t)e * 8 + kLex2Mfem[c]];
+            for (int a = 0; a < 3; a++) m.corners[((size_t)e * 8 + c) * 3 + a] = xyz[(size_t)v * 3 + a];
+        }
+}
+
+static Mesh read_mfem(const std::vector<std::string> &t)
+{
+    Mesh m;
+    size_t i = 0;
+    auto expect = [&](const char *s) {
+        if (i >= t.size() || t[i] != s) throw std::runtime_error(std::string("MFEM mesh: expected ") + s);
+        i++;
+    };
+    expect("MFEM"); expect("mesh"); expect("v1.0");
+    std::vector<double> vxyz;
+    bool have_nodes = false;
+    while (i < t.size()) {
+        const std::string key = t[i++];
+        if (key == "dimension") {
+            if (std::stoi(t[i++]) != 3) throw std::runtime_error("MFEM mesh: only dimension 3 supported");
+        } else if (key == "elements") {
+            const int n = std::stoi(t[i++]);
+            m.elems.resize((size_t)n * 8);
+            for (int e = 0; e < n; e++) {
+                i++;                                             // attribute
+                if (std::stoi(t[i++]) != 5) throw std::runtime_error("MFEM mesh: only hexahedra (geom 5) supported");
+                for (int c = 0; c < 8; c++) m.elems[(size_t)e * 8 + c] = std::stoi(t[i++]);
+            }
+        } else if (key == "boundary") {
+            const int n = std::stoi(t[i++]);
+            m.bdr.resize((size_t)n * 4); m.bdr_attr.resize(n);
+            for (int b = 0; b < n; b++) {
+                m.bdr_attr[b] = std::stoi(t[i++]);
+                if (std::stoi(t[i++]) != 3) throw std::runtime_error("MFEM mesh: only quad boundary (geom 3) supported");
+                for (int c = 0; c < 4; c++) m.bdr[(size_t)b * 4 + c] = std::stoi(t[i++]);
+            }
+        } else if (key == "vertices") {
+            m.nv = std::stoi(t[i++]);
+            if (i < t.size() && t[i] != "nodes") {
+                if (std::stoi(t[i++]) != 3) throw std::runtime_error("MFEM mesh: vertex dimension must be 3");
+                vxyz.resize((size_t)m.nv * 3);
+                for (auto &v : vxyz) v = std::stod(t[i++]);
+            }
+        } else if (key == "nodes") {
+            expect("FiniteElementSpace");
+            expect("FiniteElementCollection:");
+            if (t[i++] != "L2_T1_3D_P1") throw std::runtime_error("MFEM mesh: only L2_T1_3D_P1 nodes supported");
+            expect("VDim:"); if (std::stoi(t[i++]) != 3) throw std::runtime_error("nodes VDim != 3");
+            expect("Ordering:"); if (std::stoi(t[i++]) != 1) throw std::runtime_error("nodes Ordering != 1 (byVDIM)");
+            const size_t n = (size_t)m.ne() * 24;
+            if (t.size() - i < n) throw std::runtime_error("MFEM mesh: nodes block too short");
+            m.corners.resize(n);
+            for (auto &v : m.corners) v = std::stod(t[i++]);     // lexicographic, xyz interleaved
+            have_nodes = true;
+        } else {
+            throw std::runtime_error("MFEM mesh: unknown section " + key);
+        }
+    }
+    if (!have_nodes) {
+        if (vxyz.empty()) throw std::runtime_error("MFEM mesh: neither vertex coordinates nor nodes");
+        corners_from_vertices(m, vxyz);
+    }
+    return m;
+}
+
+static Mesh read_gmsh22(const std::vector<std::string> &t)
+{
+    Mesh m;
+    size_t i = 0;
+    auto seek = [&](const char *s) {
+        while (i < t.size() && t[i] != s) i++;
+        if (i >= t.size()) throw std::runtime_error(std::string("Gmsh: missing ") + s);
+        i++;
+    };
+    seek("$MeshFormat");
+    if (t[i].substr(0, 3) != "2.2") throw std::runtime_error("Gmsh: only format 2.2 ASCII supported");
+    seek("$Nodes");
+    const int nn = std::stoi(t[i++]);
+    std::unordered_map<long, int> remap;
+    std::vector<double> xyz((size_t)nn * 3);
+    for (int n = 0; n < nn; n++) {
+        remap[std::stol(t[i++])] = n;
+        for (int a = 0; a < 3; a++) xyz[(size_t)n * 3 + a] = std::stod(t[i++]);
+    }
+    m.nv = nn;
+    seek("$Elements");
+    const int nel = std::stoi(t[i++]);
+    for (int e = 0; e < nel; e++) {
+        i++;                                                     // element number
+        const int type = std::stoi(t[i++]);
+        const int ntags = std::stoi(t[i++]);
+        const int phys = ntags > 0 ? std::stoi(t[i]) : 0;
+        i += ntags;
+        int nnod;
+        switch (type) {
+            case 1: nnod = 2; break; case 2: nnod = 3; break; case 3: nnod = 4; break;
+            case 4: nnod = 4; break; case 5: nnod = 8; break; case 15: nnod = 1; break;
+            default: throw std::runtime_error("Gmsh: unsupported element type " + std::to_string(type));
+        }
+        if (type == 5) for (int c = 0; c < 8; c++) m.elems.push_back(remap.at(std::stol(t[i + c])));
+        else if (type == 3) { for (int c = 0; c < 4; c++) m.bdr.push_back(remap.at(std::stol(t[i + c]))); m.bdr_attr.push_back(phys); }
+        i += nnod;
+    }
+    corners_from_vertices(m, xyz);
+    return m;
+}
+
+Mesh Mesh::Read(const std::string &path)
+{
+    auto t = tokenize_skip_comments(path);
+    if (t.empty()) throw std::runtime_error("empty mesh file: " + path);
+    if (t[0] == "MFEM") return read_mfem(t);
+    if (t[0] == "$MeshFormat") return read_gmsh22(t);
+    throw std::runtime_error("unrecognised mesh format: " + path);
+}
+
+Mesh Mesh::MakeWaveTank(int nx, int ny, int nz, double Lx, double Ly, double H, bool periodic_x)
+{
+    if (periodic_x && nx < 3) throw std::runtime_error("periodic tank needs nx >= 3");
+    Mesh m;
+    const int nvx = periodic_x ? nx : nx + 1;
+    auto vid = [&](int i, int j, int k) { return (periodic_x ? i % nvx : i) + nvx * (j + (ny + 1) * k); };
+    m.nv = nvx * (ny + 1) * (nz + 1);
+    m.elems.reserve((size_t)nx * ny * nz * 8);
+    m.corners.reserve((size_t)nx * ny * nz * 24);
+    auto X = [&](int i) { return Lx * i / nx; };
+    auto Y = [&](int j) { return Ly * j / ny; };
+    auto Z = [&](int k) { return H * k / nz; };
+    for (int k = 0; k < nz; k++)
+        for (int j = 0; j < ny; j++)
+            for (int i = 0; i < nx; i++) {
+                int mf[8];
+                for (int c = 0; c < 8; c++) {
+                    const int a = c & 1, b = (c >> 1) & 1, d = (c >> 2) & 1;
+                    mf[kLex2Mfem[c]] = vid(i + a, j + b, k + d);
+                    m.corners.push_back(X(i + a)); m.corners.push_back(Y(j + b)); m.corners.push_back(Z(k + d));
+                }
+                m.elems.insert(m.elems.end(), mf, mf + 8);
+            }
+    auto face = [&](int attr, int a, int b, int c, int d) {
+        m.bdr.push_back(a); m.bdr.push_back(b); m.bdr.push_back(c); m.bdr.push_back(d);
+        m.bdr_attr.push_back(attr);
+    };
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            face(1, vid(i, j, 0), vid(i, j + 1, 0), vid(i + 1, j + 1, 0), vid(i + 1, j, 0));
+            face(2, vid(i, j, nz), vid(i + 1, j, nz), vid(i + 1, j + 1, nz), vid(i, j + 1, nz));
+        }
+    for (int k = 0; k < nz; k++)
+        for (int i = 0; i < nx; i++) {
+            face(3, vid(i, 0, k), vid(i + 1, 0, k), vid(i + 1, 0, k + 1), vid(i, 0, k + 1));
+            face(4, vid(i, ny, k), vid(i, ny, k + 1), vid(i + 1, ny, k + 1), vid(i + 1, ny, k));
+        }
+    if (!periodic_x)
+        for (int k = 0; k < nz; k++)
+            for (int j = 0; j < ny; j++) {
+                face(5, vid(nx, j, k), vid(nx, j + 1, k), vid(nx, j + 1, k + 1), vid(nx, j, k + 1));
+                face(6, vid(0, j, k), vid(0, j, k + 1), vid(0, j + 1, k + 1), vid(0, j + 1, k));
+            }
+    return m;
+}
+
+void Mesh::GetBoundingBox(double lo[3], double hi[3]) const
+{
+    for (int a = 0; a < 3; a++) { lo[a] = 1e300; hi[a] = -1e300; }
+    for (size_t i = 0; i < corners.size(); i += 3)
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], corners[i + a]); hi[a] = std::max(hi[a], corners[i + a]); }
+}
+
+void Mesh::Perturb(double amp)
+{
+    double lo[3], hi[3];
+    GetBoundingBox(lo, hi);
+    const double L[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+    double hmin = 1e300;
+    for (int e = 0; e < ne(); e++) {
+        const double *c = &corners[(size_t)e * 24];
+        hmin = std::min(hmin, std::sqrt((c[3] - c[0]) * (c[3] - c[0]) + (c[4] - c[1]) * (c[4] - c[1]) + (c[5] - c[2]) * (c[5] - c[2])));
+    }
+    for (size_t i = 0; i < corners.size(); i += 3) {
+        const double x = (corners[i] - lo[0]) / L[0], y = (corners[i + 1] - lo[1]) / L[1], z = (corners[i + 2] - lo[2]) / L[2];
+        const double s = amp * hmin * std::sin(2.0 * M_PI * x) * std::sin(M_PI * y) * std::sin(M_PI * z);
+        corners[i] += s;
+        corners[i + 1] += 0.5 * s * (L[1] / L[0]);
+        corners[i + 2] += 0.7 * s * (L[2] / L[0]);
+    }
+}
+
+namespace {
+struct Key2 {
+    uint64_t a, b;
+    bool operator==(const Key2 &o) const { return a == o.a && b == o.b; }
+};
+struct Key2Hash {
+    size_t operator()(const Key2 &k) const
+    {
+        uint64_t h = k.a * 0x9E3779B97F4A7C15ull ^ (k.b + 0xBF58476D1CE4E5B9ull + (k.a << 6) + (k.a >> 2));
+        h ^= h >> 31; h *= 0x94D049BB133111EBull; h ^= h >> 29;
+        return (size_t)h;
+    }
+};
+inline uint64_t edge_key(int a, int b) { return a < b ? ((uint64_t)a << 32) | (uint32_t)b : ((uint64_t)b << 32) | (uint32_t)a; }
+inline Key2 face_key(int a, int b, int c, int d)
+{
+    int v[4] = {a, b, c, d};
+    std::sort(v, v + 4);
+    return Key2{((uint64_t)v[0] << 32) | (uint32_t)v[1], ((uint64_t)v[2] << 32) | (uint32_t)v[3]};
+}
+// lexicographic-corner pairs of the 12 hex edges, index = axis*4 + (b0 + 2 b1)
+void edge_corners(int idx, int &ca, int &cb)
+{
+    const int axis = idx / 4, b0 = idx & 1, b1 = (idx >> 1) & 1;
+    if (axis == 0) { ca = 2 * b0 + 4 * b1; cb = ca + 1; }
+    else if (axis == 1) { ca = b0 + 4 * b1; cb = ca + 2; }
+    else { ca = b0 + 2 * b1; cb = ca + 4; }
+}
+// corner (os,ot) of face f = 2*fixed_axis + side
+int face_corner(int f, int os, int ot)
+{
+    const int ax = f / 2, side = f & 1;
+    if (ax == 0) return side + 2 * os + 4 * ot;     // x fixed: s = y, t = z
+    if (ax == 1) return os + 2 * side + 4 * ot;     // y fixed: s = x, t = z
+    return os + 2 * ot + 4 * side;                  // z fixed: s = x, t = y
+}
+}  // namespace
+
+void Mesh::UniformRefinement()
+{
+    const int ne0 = ne();
+    std::unordered_map<uint64_t, int> emid;
+    std::unordered_map<Key2, int, Key2Hash> fmid;
+    emid.reserve((size_t)ne0 * 4); fmid.reserve((size_t)ne0 * 4);
+    int nvn = nv;
+    auto edge_mid = [&](int a, int b) {
+        auto it = emid.find(edge_key(a, b));
+        if (it != emid.end()) return it->second;
+        emid.emplace(edge_key(a, b), nvn);
+        return nvn++;
+    };
+    auto face_mid = [&](int a, int b, int c, int d) {
+        const Key2 k = face_key(a, b, c, d);
+        auto it = fmid.find(k);
+        if (it != fmid.end()) return it->second;
+        fmid.emplace(k, nvn);
+        return nvn++;
+    };
+    std::vector<int> nel((size_t)ne0 * 64);
+    std::vector<double> ncor((size_t)ne0 * 8 * 24);
+    for (int e = 0; e < ne0; e++) {
+        int v[8];
+        for (int c = 0; c < 8; c++) v[c] = elems[(size_t)e * 8 + kLex2Mfem[c]];
+        const double *C = &corners[(size_t)e * 24];
+        int pid[27];
+        double px[27][3];
+        for (int c = 0; c < 3; c++)
+            for (int b = 0; b < 3; b++)
+                for (int a = 0; a < 3; a++) {
+                    const int n = a + 3 * (b + 3 * c);
+                    const int nmid = (a == 1) + (b == 1) + (c == 1);
+                    // corner bits spanned by this lattice point
+                    auto corner = [&](int sa, int sb, int sc) {
+                        const int ia = a == 1 ? sa : a / 2, ib = b == 1 ? sb : b / 2, ic = c == 1 ? sc : c / 2;
+                        return v[ia + 2 * ib + 4 * ic];
+                    };
+                    if (nmid == 0) pid[n] = corner(0, 0, 0);
+                    else if (nmid == 1) pid[n] = edge_mid(corner(0, 0, 0), corner(1, 1, 1));
+                    else if (nmid == 2) {
+                        int q[4], k = 0;
+                        // the four distinct corners: vary the two mid axes
+                        for (int s1 = 0; s1 < 2; s1++) for (int s0 = 0; s0 < 2; s0++) {
+                            int sa = 0, sb = 0, sc = 0, first = 1;
+                            if (a == 1) { sa = first ? s0 : s1; first = 0; }
+                            if (b == 1) { sb = first ? s0 : s1; first = 0; }
+                            if (c == 1) { sc = first ? s0 : s1; first = 0; }
+                            q[k++] = corner(sa, sb, sc);
+                        }
+                        pid[n] = face_mid(q[0], q[1], q[2], q[3]);
+                    } else pid[n] = nvn++;
+                    const double x = 0.5 * a, y = 0.5 * b, z = 0.5 * c;
+                    for (int d = 0; d < 3; d++) {
+                        double s = 0.0;
+                        for (int cc = 0; cc < 8; cc++) {
+                            const double w = ((cc & 1) ? x : 1 - x) * (((cc >> 1) & 1) ? y : 1 - y) * (((cc >> 2) & 1) ? z : 1 - z);
+                            s += w * C[cc * 3 + d];
+                        }
+                        px[n][d] = s;
+                    }
+                }
+        for (int ch = 0; ch < 8; ch++) {
+            const int a0 = ch & 1, b0 = (ch >> 1) & 1, c0 = (ch >> 2) & 1;
+            for (int c = 0; c < 8; c++) {
+                const int n = (a0 + (c & 1)) + 3 * ((b0 + ((c >> 1) & 1)) + 3 * (c0 + ((c >> 2) & 1)));
+                nel[((size_t)e * 8 + ch) * 8 + kLex2Mfem[c]] = pid[n];
+                for (int d = 0; d < 3; d++) ncor[(((size_t)e * 8 + ch) * 8 + c) * 3 + d] = px[n][d];
+            }
+        }
+    }
+    const int nb0 = nb();
+    std::vector<int> nbdr((size_t)nb0 * 16), nattr((size_t)nb0 * 4);
+    for (int f = 0; f < nb0; f++) {
+        const int *q = &bdr[(size_t)f * 4];
+        int mid[4];
+        for (int i = 0; i < 4; i++) mid[i] = edge_mid(q[i], q[(i + 1) % 4]);
+        const int ctr = face_mid(q[0], q[1], q[2], q[3]);
+        for (int i = 0; i < 4; i++) {
+            int *o = &nbdr[((size_t)f * 4 + i) * 4];
+            o[0] = q[i]; o[1] = mid[i]; o[2] = ctr; o[3] = mid[(i + 3) % 4];
+            nattr[(size_t)f * 4 + i] = bdr_attr[f];
+        }
+    }
+    elems.swap(nel); corners.swap(ncor); bdr.swap(nbdr); bdr_attr.swap(nattr);
+    nv = nvn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// H1 space
+// ------------------------------------------------------------------------------------------------
+H1Space::H1Space(const Mesh &mesh, int order_, int ess_attr) : order(order_), D(order_ + 1), ne(mesh.ne())
+{
+    const int p = order, D3 = D * D * D;
+    if (p < 1) throw std::runtime_error("H1Space: order must be >= 1");
+    // classify local nodes once
+    struct Node { int8_t type; int8_t ent; int16_t s, t; };   // 0 vertex, 1 edge, 2 face, 3 interior
+    std::vector<Node> nodes(D3);
+    int n_int = 0;
+    std::vector<int> int_idx(D3, -1);
+    for (int k = 0; k < D; k++)
+        for (int j = 0; j < D; j++)
+            for (int i = 0; i < D; i++) {
+                const int bi = (i == 0 || i == p), bj = (j == 0 || j == p), bk = (k == 0 || k == p);
+                const int nb = bi + bj + bk;
+                Node nd{};
+                if (nb == 3) { nd.type = 0; nd.ent = (int8_t)((i ? 1 : 0) + 2 * (j ? 1 : 0) + 4 * (k ? 1 : 0)); }
+                else if (nb == 2) {
+                    nd.type = 1;
+                    if (!bi) { nd.ent = (int8_t)(0 + (j ? 1 : 0) + 2 * (k ? 1 : 0)); nd.s = (int16_t)i; }
+                    else if (!bj) { nd.ent = (int8_t)(4 + (i ? 1 : 0) + 2 * (k ? 1 : 0)); nd.s = (int16_t)j; }
+                    else { nd.ent = (int8_t)(8 + (i ? 1 : 0) + 2 * (j ? 1 : 0)); nd.s = (int16_t)k; }
+                } else if (nb == 1) {
+                    nd.type = 2;
+                    if (bi) { nd.ent = (int8_t)(0 + (i ? 1 : 0)); nd.s = (int16_t)j; nd.t = (int16_t)k; }
+                    else if (bj) { nd.ent = (int8_t)(2 + (j ? 1 : 0)); nd.s = (int16_t)i; nd.t = (int16_t)k; }
+                    else { nd.ent = (int8_t)(4 + (k ? 1 : 0)); nd.s = (int16_t)i; nd.t = (int16_t)j; }
+                } else { nd.type = 3; int_idx[i + D * (j + D * k)] = n_int++; }
+                nodes[i + D * (j + D * k)] = nd;
+            }
+    const int ne_dofs = p - 1, nf_dofs = (p - 1) * (p - 1);
+
+    std::vector<int> vdof(mesh.nv, -1);
+    std::unordered_map<uint64_t, int> edof;
+    struct FaceRec { int base; int e0, f0, e1, f1; };
+    std::unordered_map<Key2, FaceRec, Key2Hash> fdof;
+    edof.reserve((size_t)ne * 4); fdof.reserve((size_t)ne * 4);
+    gather.resize((size_t)ne * D3);
+    int next = 0;
+    for (int e = 0; e < ne; e++) {
+        int v[8];
+        for (int c = 0; c < 8; c++) v[c] = mesh.elems[(size_t)e * 8 + kLex2Mfem[c]];
+        int ebase[12], erev[12];
+        int fbase[6], fos[6], fot[6], fswap[6];
+        // entities are numbered at first touch in the order the element's nodes meet them, so do a
+        // lazy resolve: -2 = not yet resolved for this element
+        for (int i = 0; i < 12; i++) ebase[i] = -2;
+        for (int i = 0; i < 6; i++) fbase[i] = -2;
+        const int ibase_unset = -2;
+        int ibase = ibase_unset;
+        int *g = &gather[(size_t)e * D3];
+        for (int n = 0; n < D3; n++) {
+            const Node &nd = nodes[n];
+            if (nd.type == 0) {
+                int &d = vdof[v[nd.ent]];
+                if (d < 0) d = next++;
+                g[n] = d;
+            } else if (nd.type == 1) {
+                const int ed = nd.ent;
+                if (ebase[ed] == -2) {
+                    int ca, cb;
+                    edge_corners(ed, ca, cb);
+                    const uint64_t key = edge_key(v[ca], v[cb]);
+                    auto it = edof.find(key);
+                    if (it == edof.end()) { it = edof.emplace(key, next).first; next += ne_dofs; }
+                    ebase[ed] = it->second;
+                    erev[ed] = v[ca] > v[cb];
+                }
+                const int pos = erev[ed] ? p - nd.s : nd.s;
+                g[n] = ebase[ed] + pos - 1;
+            } else if (nd.type == 2) {
+                const int f = nd.ent;
+                if (fbase[f] == -2) {
+                    int c4[4] = {face_corner(f, 0, 0), face_corner(f, 1, 0), face_corner(f, 0, 1), face_corner(f, 1, 1)};
+                    const Key2 key = face_key(v[c4[0]], v[c4[1]], v[c4[2]], v[c4[3]]);
+                    auto it = fdof.find(key);
+                    if (it == fdof.end()) { it = fdof.emplace(key, FaceRec{next, e, f, -1, -1}).first; next += nf_dofs; }
+                    else if (it->second.e0 != e || it->second.f0 != f) { it->second.e1 = e; it->second.f1 = f; }
+                    fbase[f] = it->second.base;
+                    int best = 0;
+                    for (int q = 1; q < 4; q++) if (v[c4[q]] < v[c4[best]]) best = q;
+                    fos[f] = best & 1; fot[f] = best >> 1;
+                    const int vs = v[face_corner(f, 1 - fos[f], fot[f])], vt = v[face_corner(f, fos[f], 1 - fot[f])];
+                    fswap[f] = !(vs < vt);
+                }
+                const int ds = fos[f] ? p - nd.s : nd.s, dt = fot[f] ? p - nd.t : nd.t;
+                const int a = fswap[f] ? dt : ds, b = fswap[f] ? ds : dt;
+                g[n] = fbase[f] + (a - 1) + (p - 1) * (b - 1);
+            } else {
+                if (ibase == ibase_unset) { ibase = next; next += n_int; }
+                g[n] = ibase + int_idx[n];
+            }
+        }
+        // order-1 elements have no face nodes: still register faces for boundary lookup
+        if (p == 1 || true) {
+            for (int f = 0; f < 6; f++) {
+                if (fbase[f] != -2) continue;
+                int c4[4] = {face_corner(f, 0, 0), face_corner(f, 1, 0), face_corner(f, 0, 1), face_corner(f, 1, 1)};
+                const Key2 key = face_key(v[c4[0]], v[c4[1]], v[c4[2]], v[c4[3]]);
+                auto it = fdof.find(key);
+                if (it == fdof.end()) fdof.emplace(key, FaceRec{next, e, f, -1, -1});
+                else if (it->second.e0 != e || it->second.f0 != f) { it->second.e1 = e; it->second.f1 = f; }
+            }
+        }
+    }
+    ndof = next;
+
+    // essential / surface dofs: closure of the boundary faces carrying ess_attr
+    std::vector<int> surf_of(ndof, -1);
+    Basis1D bs(p);
+    for (int b = 0; b < mesh.nb(); b++) {
+        if (mesh.bdr_attr[b] != ess_attr) continue;
+        const int *q = &mesh.bdr[(size_t)b * 4];
+        auto it = fdof.find(face_key(q[0], q[1], q[2], q[3]));
+        if (it == fdof.end()) throw std::runtime_error("H1Space: boundary face not found among element faces");
+        const int es[2] = {it->second.e0, it->second.e1}, fs[2] = {it->second.f0, it->second.f1};
+        for (int side = 0; side < 2; side++) {
+            const int e = es[side], f = fs[side];
+            if (e < 0) continue;
+            const int ax = f / 2, fixed = (f & 1) ? p : 0;
+            const double *C = &mesh.corners[(size_t)e * 24];
+            for (int t = 0; t < D; t++)
+                for (int s = 0; s < D; s++) {
+                    int i, j, k;
+                    if (ax == 0) { i = fixed; j = s; k = t; }
+                    else if (ax == 1) { i = s; j = fixed; k = t; }
+                    else { i = s; j = t; k = fixed; }
+                    const int gdof = gather[(size_t)e * D3 + i + D * (j + D * k)];
+                    if (surf_of[gdof] >= 0) continue;
+                    surf_of[gdof] = (int)surf2vol.size();
+                    surf2vol.push_back(gdof);
+                    const double x = bs.nodes[i], y = bs.nodes[j], z = bs.nodes[k];
+                    double pt[2] = {0.0, 0.0};
+                    for (int c = 0; c < 8; c++) {
+                        const double w = ((c & 1) ? x : 1 - x) * (((c >> 1) & 1) ? y : 1 - y) * (((c >> 2) & 1) ? z : 1 - z);
+                        pt[0] += w * C[c * 3]; pt[1] += w * C[c * 3 + 1];
+                    }
+                    surf_xy.push_back(pt[0]); surf_xy.push_back(pt[1]);
+                }
+        }
+    }
+    ess = surf2vol;
+    std::sort(ess.begin(), ess.end());
+    for (int e = 0; e < ne; e++) {
+        const int *g = &gather[(size_t)e * D3];
+        for (int n = 0; n < D3; n++) if (surf_of[g[n]] >= 0) { surf_elems.push_back(e); break; }
+    }
+}
+
+void H1Space::NodeCoordinates(const Mesh &mesh, std::vector<double> &xyz) const
+{
+    const int D3 = D * D * D;
+    Basis1D bs(order);
+    xyz.assign((size_t)ndof * 3, 0.0);
+    for (int e = 0; e < ne; e++) {
+        const double *C = &mesh.corners[(size_t)e * 24];
+        for (int k = 0; k < D; k++)
+            for (int j = 0; j < D; j++)
+                for (int i = 0; i < D; i++) {
+                    const double x = bs.nodes[i], y = bs.nodes[j], z = bs.nodes[k];
+                    double pt[3] = {0, 0, 0};
+                    for (int c = 0; c < 8; c++) {
+                        const double w = ((c & 1) ? x : 1 - x) * (((c >> 1) & 1) ? y : 1 - y) * (((c >> 2) & 1) ? z : 1 - z);
+                        for (int a = 0; a < 3; a++) pt[a] += w * C[c * 3 + a];
+                    }
+                    const int gd = gather[(size_t)e * D3 + i + D * (j + D * k)];
+                    for (int a = 0; a < 3; a++) xyz[(size_t)gd * 3 + a] = pt[a];
+                }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Partitioning
+// ------------------------------------------------------------------------------------------------
+static void rcb(const std::vector<double> &cen, std::vector<int> &idx, int lo, int hi, int part0, int nparts,
+                std::vector<int> &out)
+{
+    if (nparts == 1) { for (int i = lo; i < hi; i++) out[idx[i]] = part0; return; }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int i = lo; i < hi; i++)
+        for (int a = 0; a < 3; a++) { const double v = cen[(size_t)idx[i] * 3 + a]; mn[a] = std::min(mn[a], v); mx[a] = std::max(mx[a], v); }
+    int ax = 0;
+    for (int a = 1; a < 3; a++) if (mx[a] - mn[a] > (mx[ax] - mn[ax]) * (1.0 + 1e-9)) ax = a;
+    const int nl = nparts / 2, nr = nparts - nl;
+    const int mid = lo + (int)(((long)(hi - lo) * nl) / nparts);
+    std::sort(idx.begin() + lo, idx.begin() + hi, [&](int a, int b) {
+        const double va = cen[(size_t)a * 3 + ax], vb = cen[(size_t)b * 3 + ax];
+        const double tol = 1e-12 * (mx[ax] - mn[ax] + 1e-300);
+        if (std::fabs(va - vb) > tol) return va < vb;
+        return a < b;
+    });
+    rcb(cen, idx, lo, mid, part0, nl, out);
+    rcb(cen, idx, mid, hi, part0 + nl, nr, out);
+}
+
+std::vector<int> PartitionElementsRCB(const Mesh &mesh, int nparts)
+{
+    const int ne = mesh.ne();
+    std::vector<double> cen((size_t)ne * 3, 0.0);
+    for (int e = 0; e < ne; e++)
+        for (int c = 0; c < 8; c++)
+            for (int a = 0; a < 3; a++) cen[(size_t)e * 3 + a] += 0.125 * mesh.corners[((size_t)e * 8 + c) * 3 + a];
+    std::vector<int> idx(ne), out(ne, 0);
+    std::iota(idx.begin(), idx.end(), 0);
+    if (nparts > 1) rcb(cen, idx, 0, ne, 0, nparts, out);
+    return out;
+}
+
+static void build_halo(int nranks, int rank, const std::vector<uint64_t> &mask, const std::vector<int> &gid,
+                       std::vector<int> &nbr_rank, std::vector<int> &nbr_offset, std::vector<int> &send,
+                       std::vector<int> &shared, std::vector<int> &red_off, std::vector<int> &red_src)
+{
+    const int n = (int)mask.size();
+    const uint64_t me = 1ull << rank;
+    // candidates sorted by global id so both sides of a pair agree on the order
+    std::vector<int> cand;
+    for (int l = 0; l < n; l++) if (mask[l] & ~me) cand.push_back(l);
+    std::sort(cand.begin(), cand.end(), [&](int a, int b) { return gid[a] < gid[b]; });
+    nbr_rank.clear(); nbr_offset.assign(1, 0); send.clear();
+    std::vector<std::vector<int>> pos(nranks);       // per neighbour: position of cand[i] in its list or -1
+    for (int s = 0; s < nranks; s++) {
+        if (s == rank) continue;
+        std::vector<int> list;
+        std::vector<int> ps(cand.size(), -1);
+        for (size_t i = 0; i < cand.size(); i++)
+            if (mask[cand[i]] & (1ull << s)) { ps[i] = (int)list.size(); list.push_back(cand[i]); }
+        if (list.empty()) continue;
+        nbr_rank.push_back(s);
+        send.insert(send.end(), list.begin(), list.end());
+        nbr_offset.push_back((int)send.size());
+        pos[s].swap(ps);
+    }
+    shared.clear(); red_off.assign(1, 0); red_src.clear();
+    for (size_t i = 0; i < cand.size(); i++) {
+        shared.push_back(cand[i]);
+        for (int s = 0; s < nranks; s++) {
+            if (!(mask[cand[i]] & (1ull << s))) continue;
+            if (s == rank) { red_src.push_back(-1); continue; }
+            const int k = (int)(std::find(nbr_rank.begin(), nbr_rank.end(), s) - nbr_rank.begin());
+            red_src.push_back(nbr_offset[k] + pos[s][i]);
+        }
+        red_off.push_back((int)red_src.size());
+    }
+}
+
+Partition::Partition(const Mesh &mesh, const H1Space &space, int nranks_, int rank_) : nranks(nranks_), rank(rank_)
+{
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) throw std::runtime_error("Partition: bad rank/nranks");
+    const int D3 = space.D * space.D * space.D;
+    const int neg = space.ne;
+    elem_rank = PartitionElementsRCB(mesh, nranks);
+    std::vector<int> g2l(space.ndof, -1);
+    if (nranks == 1) {   // serial: local numbering IS the global numbering (what l2g of any partition refers to)
+        l2g.resize(space.ndof);
+        std::iota(l2g.begin(), l2g.end(), 0);
+        g2l = l2g;
+    }
+    for (int e = 0; e < neg; e++) {
+        if (elem_rank[e] != rank) continue;
+        elems.push_back(e);
+        for (int n = 0; n < D3; n++) {
+            const int g = space.gather[(size_t)e * D3 + n];
+            if (g2l[g] < 0) { g2l[g] = (int)l2g.size(); l2g.push_back(g); }
+            gather.push_back(g2l[g]);
+        }
+        corners.insert(corners.end(), mesh.corners.begin() + (size_t)e * 24, mesh.corners.begin() + (size_t)(e + 1) * 24);
+    }
+    const int nl = (int)l2g.size();
+    std::vector<uint64_t> mask(nl, 0);
+    std::vector<int> gsurf(space.ndof, -1);
+    for (size_t s = 0; s < space.surf2vol.size(); s++) gsurf[space.surf2vol[s]] = (int)s;
+    std::vector<int> mult_l(nl, 0);
+    for (int e = 0; e < neg; e++) {
+        const uint64_t bit = 1ull << elem_rank[e];
+        for (int n = 0; n < D3; n++) {
+            const int l = g2l[space.gather[(size_t)e * D3 + n]];
+            if (l >= 0) { mask[l] |= bit; mult_l[l]++; }
+        }
+    }
+    owned.resize(nl);
+    for (int l = 0; l < nl; l++) owned[l] = ((mask[l] & (~mask[l] + 1)) == (1ull << rank));
+    for (int g : space.ess) if (g2l[g] >= 0) ess.push_back(g2l[g]);
+    std::sort(ess.begin(), ess.end());
+    build_halo(nranks, rank, mask, l2g, nbr_rank, nbr_offset, send_dofs, shared_dofs, red_off, red_src);
+    // surface: local dofs that are surface dofs globally, ascending global surface index
+    std::vector<std::pair<int, int>> sl;
+    for (int l = 0; l < nl; l++) if (gsurf[l2g[l]] >= 0) sl.emplace_back(gsurf[l2g[l]], l);
+    std::sort(sl.begin(), sl.end());
+    std::vector<uint64_t> smask;
+    std::vector<int> vol2surf(nl, -1);
+    for (auto &pr : sl) {
+        vol2surf[pr.second] = (int)surf2vol.size();
+        surf_g.push_back(pr.first);
+        surf2vol.push_back(pr.second);
+        surf_xy.push_back(space.surf_xy[(size_t)pr.first * 2]);
+        surf_xy.push_back(space.surf_xy[(size_t)pr.first * 2 + 1]);
+        surf_mult.push_back(mult_l[pr.second]);
+        surf_owned.push_back(owned[pr.second]);
+        smask.push_back(mask[pr.second]);
+    }
+    build_halo(nranks, rank, smask, surf_g, s_nbr_rank, s_nbr_offset, s_send, s_shared, s_red_off, s_red_src);
+    for (int le = 0; le < (int)elems.size(); le++)
+        for (int n = 0; n < D3; n++)
+            if (vol2surf[gather[(size_t)le * D3 + n]] >= 0) { surf_elems.push_back(le); break; }
+    n_true_global = space.ndof;
+    n_surf_global = (long)space.surf2vol.size();
+}
+
+}  // namespace lpf

@@ -942,3 +942,41 @@ def hash_noise(n, seed=0x5EED1234):
     with np.errstate(over='ignore'):
         h = splitmix64(np.arange(n, dtype=np.uint64) ^ np.uint64(seed))
     return (h >> np.uint64(11)).astype(np.float64) * (2.0 / (1 << 53)) - 1.0
+
+
+def write_mfem_mesh(mesh: HexMesh, path, with_nodes=None):
+    """Writes MFEM mesh v1.0 (own writer; used to produce self-contained test inputs).  with_nodes=True
+    emits the discontinuous L2_T1_3D_P1 `nodes` block (needed for periodic meshes), False plain vertices."""
+    if with_nodes is None:
+        # periodic meshes cannot carry geometry in the vertices
+        vx = np.full((mesh.nv, 3), np.nan)
+        ok = True
+        ev = mesh.elems[:, LEX2MFEM]
+        for c in range(8):
+            cur = vx[ev[:, c]]
+            new = mesh.corners[:, c]
+            bad = ~np.isnan(cur[:, 0]) & (np.abs(cur - new).max(axis=1) > 1e-13)
+            if bad.any():
+                ok = False
+                break
+            vx[ev[:, c]] = new
+        with_nodes = not ok
+    with open(path, 'w') as f:
+        f.write('MFEM mesh v1.0\n\ndimension\n3\n\nelements\n%d\n' % mesh.ne)
+        for e in range(mesh.ne):
+            f.write('1 5 ' + ' '.join(str(int(v)) for v in mesh.elems[e]) + '\n')
+        f.write('\nboundary\n%d\n' % len(mesh.bdr_attr))
+        for b in range(len(mesh.bdr_attr)):
+            f.write('%d 3 ' % mesh.bdr_attr[b] + ' '.join(str(int(v)) for v in mesh.bdr[b]) + '\n')
+        f.write('\nvertices\n%d\n' % mesh.nv)
+        if with_nodes:
+            f.write('\nnodes\nFiniteElementSpace\nFiniteElementCollection: L2_T1_3D_P1\nVDim: 3\nOrdering: 1\n\n')
+            for e in range(mesh.ne):
+                for c in range(8):
+                    f.write('%.17g %.17g %.17g\n' % tuple(mesh.corners[e, c]))
+        else:
+            vx = np.zeros((mesh.nv, 3))
+            vx[mesh.elems[:, LEX2MFEM].reshape(-1)] = mesh.corners.reshape(-1, 3)
+            f.write('3\n')
+            for v in range(mesh.nv):
+                f.write('%.17g %.17g %.17g\n' % tuple(vx[v]))

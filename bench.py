@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- PA Laplace matvec GDOF/s (+ PCG time per RK4 step) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's CPU path (C restatement, all host threads)
+
+A "step" is one constrained operator apply y = (P^T A P)_c x on the whole mesh (the operation CGSolver
+calls once per iteration).  Workload at N=1: wave-tank-big8 (128x2x16 hexes, x-periodic)
+uniformly refined twice, H1 order 4: 262 144 hexes, 17 369 088 dofs, 2.7 GB of q-data (>> 126 MB L2, so
+no L2 flush is needed between iterations).  N>1: weak scaling, the tank is N times longer (128 N cells in
+x) and is cut into N x-slabs, one per GPU, halo-summed over NCCL after every apply.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pa_laplace_matvec_gdofs"
+UNIT = "GDOF/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--refine", type=int, default=2, help="uniform refinements of the 128x2x16 tank")
+    ap.add_argument("--variant", type=int, default=0, help="apply kernel variant (tuning)")
+    ap.add_argument("--no-rk4", action="store_true", help="skip the PCG-per-RK-step measurement")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rk4-refine", type=int, default=1)
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"wave-tank-big8(128x2x16,x-periodic) r={a.refine} order={a.order}"
+
+
+def algorithmic_bytes(ne, ndof, p):
+    """NE (48 Q^3 + 4 D^3) + 16 N_L  (q-data + gather map + read x + write y)."""
+    D, Q = p + 1, p + 2
+    return ne * (48 * Q ** 3 + 4 * D ** 3) + 16 * ndof
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(p):
+    """dram bytes per launch of the apply kernel from the committed ncu capture, if one exists."""
+    f = os.path.join(ROOT, "profiles", "apply_traffic.json")
+    if os.path.exists(f):
+        d = json.load(open(f))
+        return d.get(f"order{p}")
+    return None
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the C restatement of MFEM's CPU PA path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_apply_gdofs(order, refine, seconds=12.0, threads=None):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c                                 # checker / baseline only
+    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
+    nthreads = threads or os.cpu_count()
+    oracle_c.set_threads(nthreads)
+    sp = lpf.Space(lpf.Mesh.wave_tank(128, 2, 16).refine(refine), order)
+    cop = oracle_c.COperator(order, sp.corners, sp.gather, sp.ndof, lpf.basis_tables(order))
+    x = np.random.default_rng(0).random(sp.ndof) - 0.5
+    cop.mult(x)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        cop.mult(x)
+        n += 1
+        el = time.perf_counter() - t0
+        if el > seconds and n >= 2:
+            break
+    return sp.ndof * n / el / 1e9, nthreads, f"{n} applies on wave-tank-big8 r={refine} order={order} ({sp.ne} hexes, {sp.ndof} dofs)", el / n
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, a.steps)
+    ref = min(a.refine, 1)
+    # each "step" of the reference arm is a bounded sample: one apply on the r<=1 tank
+    g, nth, sample, sec = cpu_apply_gdofs(a.order, ref, seconds=min(60.0, 1.5 * (steps + a.warmup)))
+    line = {"impl": "reference", "metric": METRIC, "value": g, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "sample": sample},
+            "cpu_baseline": {"value": g, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
+            "e2e": {"value": g, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "MFEM/hypre/MPI are not installable here; this is the C/OpenMP restatement of MFEM's CPU PA path (oracle/pa_oracle.c)"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    torch.cuda.set_stream(torch.cuda.Stream())      # explicit stream shared by torch events and the C-ABI calls
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    p = a.order
+    mesh = lpf.Mesh.wave_tank(128 * world, 2, 16, Lx=1.0 * world).refine(a.refine)
+    sp = lpf.Space(mesh, p, nranks=world, rank=rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = lpf.Context(sp, device=local, stream=stream)
+    ctx.set_option("apply_variant", a.variant)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()))
+    ctx.pa_setup()
+    n = sp.ndof
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    y = torch.empty_like(x)
+    ndof_global = int(sp.n_true_global)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, a.warmup)):
+        ctx.apply_T(x, y)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(a.steps):
+        ctx.apply_T(x, y)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - l0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t[0])
+    # element kernel alone (roofline numerator), CUDA events on the launching stream inside the library
+    _, ms_k, _ = ctx.time_apply(x, y, a.steps)
+    tk = torch.tensor([ms_k], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    ms_kernel = float(tk[0]) / a.steps
+
+    # end to end through the C-ABI with HOST buffers (pinned), H2D + apply + D2H per step
+    xh = torch.empty(n, dtype=torch.float64).pin_memory()
+    yh = torch.empty(n, dtype=torch.float64).pin_memory()
+    xh.copy_(x.cpu())
+    e2e_steps = max(2, min(a.steps, 10))
+    ctx.apply_T_host(xh, yh)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.apply_T_host(xh, yh)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = ndof_global * e2e_steps / float(te[0]) / 1e9
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    # PCG time per RK4 step (strongscaling.cpp-like protocol: rel 1e-12, RK4, dt = T/150) on the r=1 tank
+    rk = None
+    if not a.no_rk4 and world == 1:
+        rk = rk4_measure(lpf, torch, a, local, stream)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = ndof_global * a.steps / (ms_max * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    ab = algorithmic_bytes(sp.ne, sp.ndof, p)
+    achieved = ab / (ms_kernel * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "hexes_per_gpu": sp.ne, "dofs_global": ndof_global, "order": p,
+                   "l2_policy": "inputs larger than L2 (q-data %.2f GB per GPU), no flush" % (sp.ne * 48 * (p + 2) ** 3 / 1e9),
+                   "parallelism": f"x-slab domain decomposition x{world}, NCCL halo-sum" if world > 1 else "single GPU",
+                   "apply_variant": a.variant},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(p), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                     "kernel_ms": ms_kernel, "kernel": "pa_apply_kernel"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
+                "steps": e2e_steps, "api": "lpf_apply_T_host (pinned host x -> device -> apply -> host y)"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if rk is not None:
+        line["pcg_per_rk4_step"] = rk
+    if not a.no_cpu:
+        g, nth, sample, _ = cpu_apply_gdofs(p, min(a.refine, 1), seconds=12.0)
+        line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def rk4_measure(lpf, torch, a, local, stream):
+    p = a.order
+    mesh = lpf.Mesh.wave_tank(128, 2, 16).refine(a.rk4_refine)
+    sp = lpf.Space(mesh, p)
+    ctx = lpf.Context(sp, device=local, stream=stream)
+    ctx.pa_setup()
+    ctx.jacobi_setup()
+    w = lpf.wave_params()
+    dt = w["T"] / 150
+    ctx.rhs_setup(lpf.make_rhs_params(w, rel_tol=1e-12, max_iter=2000))
+    xs, ys = sp.surf_xy[:, 0], sp.surf_xy[:, 1]
+    ph = -w["k"] * (w["kx_dir"] * xs + w["ky_dir"] * ys)
+    st = np.concatenate([0.5 * w["H"] * np.cos(ph), -0.5 * w["H"] * w["cwave"] / np.tanh(w["kh"]) * np.sin(ph)])
+    sd = torch.from_numpy(st).cuda()
+    t = ctx.rk4_step(sd, 0.0, dt)               # warm-up step (ss.cpp:253)
+    torch.cuda.synchronize()
+    l0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nst = 2
+    ev0.record()
+    for _ in range(nst):
+        t = ctx.rk4_step(sd, t, dt)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / nst
+    infos = ctx.last_solve_info()
+    its = [i.iterations for i in infos]
+    out = {"workload": f"wave-tank-big8 r={a.rk4_refine} order={p} ({sp.ne} hexes, {sp.ndof} dofs), RK4 dt=T/150, Jacobi-PCG rel 1e-12",
+           "ms_per_rk4_step": ms, "cg_iterations_per_stage": its, "converged": [int(i.converged) for i in infos],
+           "ms_per_cg_iteration": ms / max(1, sum(its)), "gpu_launches_per_step": int((ctx.launches - l0) / nst)}
+    ctx.close()
+    return out
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)

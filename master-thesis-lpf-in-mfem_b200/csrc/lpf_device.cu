@@ -66,6 +66,7 @@ struct lpf_ctx {
     // options
     int variant = 0;          // apply kernel variant (elements per CTA / prefetch), see apply_launch
     int use_graph = 1, chunk = 16, skip_zero_apply = 1;
+    int ess_general = 0;      // lpf_pcg: search directions may be non-zero on essential dofs
     // geometry / maps
     double *corners = nullptr, *jac = nullptr, *qd = nullptr;
     int *gmap = nullptr, *gmap_c = nullptr, *ess = nullptr;
@@ -93,7 +94,7 @@ struct lpf_ctx {
     double *hx = nullptr, *hy = nullptr;
     // CUDA graph of one PCG chunk
     cudaGraphExec_t pcg_graph = nullptr;
-    int pcg_graph_chunk = 0;
+    int pcg_graph_chunk = 0, pcg_graph_general = 0, pcg_graph_launches = 0;
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -136,6 +137,9 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
             if (v == 2) return apply_launch_t<4, 4, false, EVEC, 1>(c, gmap, x, y, den, status);
             if (v == 3) return apply_launch_t<4, 2, true, EVEC, 1>(c, gmap, x, y, den, status);
             if (v == 4) return apply_launch_t<4, 8, false, EVEC, 1>(c, gmap, x, y, den, status);
+            if (v == 5) return apply_launch_t<4, 1, true, EVEC, 1>(c, gmap, x, y, den, status);
+            if (v == 6) return apply_launch_t<4, 3, true, EVEC, 1>(c, gmap, x, y, den, status);
+            if (v == 7) return apply_launch_t<4, 2, false, EVEC, 1>(c, gmap, x, y, den, status);
             return apply_launch_t<4, 4, true, EVEC, 1>(c, gmap, x, y, den, status);
         case 5: return v == 1 ? apply_launch_t<5, 2, true, EVEC, 1>(c, gmap, x, y, den, status)
                               : apply_launch_t<5, 4, true, EVEC, 1>(c, gmap, x, y, den, status);
@@ -485,6 +489,16 @@ int lpf_jacobi_dinv(lpf_ctx *c, double *out)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
+int ess_fix(lpf_ctx *c)
+{
+    if (!c->ess_general || c->ness == 0) return LPF_OK;
+    const int g = std::max(1, std::min((c->ness + 255) / 256, 256));
+    pcg_ess_fix_kernel<<<g, 256, 0, c->stream>>>(c->ness, c->ess, c->d, c->ad, c->owned, c->den_slots, c->st);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
 // one CG iteration body: update (+ dot), direction, apply (+ den); all skip themselves once status != 0
 int pcg_iteration(lpf_ctx *c)
 {
@@ -503,6 +517,7 @@ int pcg_iteration(lpf_ctx *c)
     pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
     c->launches++;
     LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+    LPF_TRY(ess_fix(c));
     if (multi) {
         LPF_TRY(halo_sum(c, c->halo, c->ad));
         pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
@@ -519,7 +534,7 @@ int pcg_chunk(lpf_ctx *c)
         for (int i = 0; i < c->chunk; i++) LPF_TRY(pcg_iteration(c));
         return LPF_OK;
     }
-    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk) {
+    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk || c->pcg_graph_general != c->ess_general) {
         if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
         cudaGraph_t graph = nullptr;
         const long l0 = c->launches;
@@ -527,15 +542,17 @@ int pcg_chunk(lpf_ctx *c)
         int rc = LPF_OK;
         for (int i = 0; i < c->chunk && rc == LPF_OK; i++) rc = pcg_iteration(c);
         cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        c->pcg_graph_launches = (int)(c->launches - l0);
         c->launches = l0;
         if (rc != LPF_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
         CUDA_TRY(ce);
         CUDA_TRY(cudaGraphInstantiate(&c->pcg_graph, graph, 0));
         cudaGraphDestroy(graph);
         c->pcg_graph_chunk = c->chunk;
+        c->pcg_graph_general = c->ess_general;
     }
     CUDA_TRY(cudaGraphLaunch(c->pcg_graph, c->stream));
-    c->launches += (long)c->chunk * (c->nranks > 1 ? 7 : 3);
+    c->launches += c->pcg_graph_launches;
     return LPF_OK;
 }
 
@@ -572,6 +589,7 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         c->launches++;
     }
     LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+    LPF_TRY(ess_fix(c));
     if (multi) {
         LPF_TRY(halo_sum(c, c->halo, c->ad));
         pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
@@ -613,6 +631,7 @@ int solve_from_X(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, lpf_p
         copy_at_kernel<<<(c->ness + 255) / 256, 256, 0, c->stream>>>(c->ness, c->ess, c->X, c->Bv);
         c->launches++;
     }
+    c->ess_general = 0;
     LPF_TRY(pcg_run(c, rel_tol, abs_tol, max_iter, true, info));
     if (info) info->applies += 1;
     return LPF_OK;
@@ -630,6 +649,7 @@ int lpf_pcg(lpf_ctx *c, const double *B, double *X, double rel_tol, double abs_t
     const size_t nb = sizeof(double) * c->ndof;
     CUDA_TRY(cudaMemcpyAsync(c->X, X, nb, cudaMemcpyDeviceToDevice, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->Bv, B, nb, cudaMemcpyDeviceToDevice, c->stream));
+    c->ess_general = 1;
     LPF_TRY(pcg_run(c, rel_tol, abs_tol, max_iter, false, info));
     CUDA_TRY(cudaMemcpyAsync(X, c->X, nb, cudaMemcpyDeviceToDevice, c->stream));
     return LPF_OK;

@@ -168,6 +168,25 @@ __global__ void pcg_dir_kernel(int n, const double *__restrict__ z, double *__re
     }
 }
 
+// General right-hand sides (lpf_pcg): the search direction can be non-zero on essential dofs, where the
+// constrained operator is the identity: ad[ess] = d[ess] and (d, A_c d) gains sum d[ess]^2.  (The Laplace
+// solve of the RHS never needs this: there r[ess] == 0 exactly, so d[ess] == 0 for all iterations.)
+__global__ void pcg_ess_fix_kernel(int ness, const int *__restrict__ ess, const double *__restrict__ d,
+                                   double *__restrict__ ad, const uint8_t *__restrict__ owned,
+                                   double *__restrict__ den_slots, const PcgState *st)
+{
+    if (st->status != PCG_RUNNING) return;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ness; i += gridDim.x * blockDim.x) {
+        const int e = ess[i];
+        const double v = d[e];
+        ad[e] = v;
+        if (!owned || owned[e]) acc = fma(v, v, acc);
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) atomicAdd(den_slots + (blockIdx.x & (LPF_DEN_SLOTS - 1)), acc);
+}
+
 // ---- small helpers ------------------------------------------------------------------------------
 __global__ void copy_at_kernel(int n, const int *__restrict__ idx, const double *__restrict__ src, double *__restrict__ dst)
 {

@@ -52,6 +52,9 @@ def cuda(lpf):
     if not torch.cuda.is_available() or lpf.lib.lpf_device_count() < 1:
         pytest.skip("no CUDA device")
     torch.cuda.set_device(0)
+    # the library enqueues on the stream it is given; a NULL stream means "create your own", so run the
+    # whole session on an explicit non-default torch stream shared by torch ops and the C-ABI calls
+    torch.cuda.set_stream(torch.cuda.Stream())
     return torch
 
 

@@ -13,6 +13,8 @@
 #include "../host/lpf_host.hpp"
 #include "lpf_comm.hpp"
 #include "pa_kernels.cuh"
+#include "pa_apply_pipe.cuh"
+#include "pa_apply_tma.cuh"
 #include "vec_kernels.cuh"
 
 #define CUDA_TRY(call)                                                                              \
@@ -66,6 +68,7 @@ struct lpf_ctx {
     // options
     int variant = 0;          // apply kernel variant (elements per CTA / prefetch), see apply_launch
     int use_graph = 1, chunk = 16, skip_zero_apply = 1;
+    int max_ctas = 0;
     int ess_general = 0;      // lpf_pcg: search directions may be non-zero on essential dofs
     // geometry / maps
     double *corners = nullptr, *jac = nullptr, *qd = nullptr;
@@ -122,6 +125,54 @@ int apply_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, doub
     return LPF_OK;
 }
 
+template <int P, int E, int MINB>
+int apply_pipe_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
+{
+    using C = ApplyCfg<P, E>;
+    static int blocks_per_sm[16] = {0};
+    auto kd = pa_apply_pipe_kernel<P, E, true, MINB>;
+    auto kn = pa_apply_pipe_kernel<P, E, false, MINB>;
+    int &bps = blocks_per_sm[c->dev & 15];
+    if (bps == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
+        if (bps < 1) bps = 1;
+    }
+    const int nb = (c->ne + E - 1) / E;
+    if (nb == 0) return LPF_OK;
+    const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
+    if (den) kd<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
+    else kn<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+template <int P, int E, int MINB>
+int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
+{
+    using C = TmaCfg<P, E>;
+    static int blocks_per_sm[16] = {0};
+    auto kd = pa_apply_tma_kernel<P, E, true, MINB>;
+    auto kn = pa_apply_tma_kernel<P, E, false, MINB>;
+    int &bps = blocks_per_sm[c->dev & 15];
+    if (bps == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
+        if (bps < 1) bps = 1;
+    }
+    const int nb = (c->ne + E - 1) / E;
+    if (nb == 0) return LPF_OK;
+    const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
+    if (den) kd<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
+    else kn<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
 // variant 0 = default for the order; other values pick alternative (E, prefetch) pairs for tuning
 template <bool EVEC>
 int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
@@ -133,6 +184,26 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
         case 3: return v == 1 ? apply_launch_t<3, 4, true, EVEC, 1>(c, gmap, x, y, den, status)
                               : apply_launch_t<3, 8, true, EVEC, 1>(c, gmap, x, y, den, status);
         case 4:
+            if (!EVEC && v >= 20) {
+                if (v == 20) return apply_tma_launch_t<4, 2, 4>(c, gmap, x, y, den, status);
+                if (v == 21) return apply_tma_launch_t<4, 2, 5>(c, gmap, x, y, den, status);
+                if (v == 22) return apply_tma_launch_t<4, 3, 3>(c, gmap, x, y, den, status);
+                if (v == 23) return apply_tma_launch_t<4, 4, 2>(c, gmap, x, y, den, status);
+                if (v == 24) return apply_tma_launch_t<4, 8, 1>(c, gmap, x, y, den, status);
+                if (v == 25) return apply_tma_launch_t<4, 1, 6>(c, gmap, x, y, den, status);
+                if (v == 26) return apply_tma_launch_t<4, 2, 6>(c, gmap, x, y, den, status);
+                if (v == 27) return apply_tma_launch_t<4, 4, 3>(c, gmap, x, y, den, status);
+            }
+            if (!EVEC && v >= 10) {
+                if (v == 10) return apply_pipe_launch_t<4, 2, 4>(c, gmap, x, y, den, status);
+                if (v == 11) return apply_pipe_launch_t<4, 2, 5>(c, gmap, x, y, den, status);
+                if (v == 12) return apply_pipe_launch_t<4, 4, 2>(c, gmap, x, y, den, status);
+                if (v == 13) return apply_pipe_launch_t<4, 4, 3>(c, gmap, x, y, den, status);
+                if (v == 14) return apply_pipe_launch_t<4, 3, 3>(c, gmap, x, y, den, status);
+                if (v == 15) return apply_pipe_launch_t<4, 8, 1>(c, gmap, x, y, den, status);
+                if (v == 16) return apply_pipe_launch_t<4, 8, 2>(c, gmap, x, y, den, status);
+                if (v == 17) return apply_pipe_launch_t<4, 2, 6>(c, gmap, x, y, den, status);
+            }
             if (v == 1) return apply_launch_t<4, 8, true, EVEC, 1>(c, gmap, x, y, den, status);
             if (v == 2) return apply_launch_t<4, 4, false, EVEC, 1>(c, gmap, x, y, den, status);
             if (v == 3) return apply_launch_t<4, 2, true, EVEC, 1>(c, gmap, x, y, den, status);
@@ -214,19 +285,26 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     }
     if (d->corners) LPF_TRY(upload(c->corners, d->corners, (size_t)c->ne * 24, &c->bytes));
     if (d->jac) LPF_TRY(upload(c->jac, d->jac, (size_t)c->ne * Q3 * 9, &c->bytes));
-    LPF_TRY(upload(c->gmap, d->gather, (size_t)c->ne * D3, &c->bytes));
+    const int DP3 = (D3 + 3) & ~3;       // rows padded to 16 bytes (bulk-copy granularity)
+    {
+        std::vector<int> gp((size_t)c->ne * DP3, 0);
+        for (int e = 0; e < c->ne; e++)
+            for (int k = 0; k < D3; k++) gp[(size_t)e * DP3 + k] = d->gather[(size_t)e * D3 + k];
+        LPF_TRY(upload(c->gmap, gp.data(), gp.size(), &c->bytes));
+    }
     {   // constrained map: essential dofs encoded as ~dof (gather reads 0, scatter skips)
         std::vector<uint8_t> em((size_t)c->ndof, 0);
         for (int i = 0; i < c->ness; i++) {
             if (d->ess[i] < 0 || d->ess[i] >= c->ndof) { lpf::set_error("lpf_create: essential dof out of range"); return LPF_ERR_ARG; }
             em[d->ess[i]] = 1;
         }
-        std::vector<int> gc((size_t)c->ne * D3);
-        for (size_t i = 0; i < gc.size(); i++) {
-            const int g = d->gather[i];
-            if (g < 0 || g >= c->ndof) { lpf::set_error("lpf_create: gather index out of range"); return LPF_ERR_ARG; }
-            gc[i] = em[g] ? ~g : g;
-        }
+        std::vector<int> gc((size_t)c->ne * DP3, 0);
+        for (int e = 0; e < c->ne; e++)
+            for (int k = 0; k < D3; k++) {
+                const int g = d->gather[(size_t)e * D3 + k];
+                if (g < 0 || g >= c->ndof) { lpf::set_error("lpf_create: gather index out of range"); return LPF_ERR_ARG; }
+                gc[(size_t)e * DP3 + k] = em[g] ? ~g : g;
+            }
         LPF_TRY(upload(c->gmap_c, gc.data(), gc.size(), &c->bytes));
         LPF_TRY(upload(c->essmask, em.data(), em.size(), &c->bytes));
         LPF_TRY(upload(c->ess, d->ess, (size_t)c->ness, &c->bytes));
@@ -361,6 +439,7 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "use_graph") c->use_graph = (int)value;
     else if (k == "pcg_chunk") { if (value < 1) { lpf::set_error("pcg_chunk must be >= 1"); return LPF_ERR_ARG; } c->chunk = (int)value; }
     else if (k == "skip_zero_apply") c->skip_zero_apply = (int)value;
+    else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
     if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
     return LPF_OK;

@@ -1,0 +1,291 @@
+// Persistent PA apply kernel with the quadrature data and the gather map staged in shared memory by bulk
+// asynchronous copies (TMA 1-D: cp.async.bulk ... mbarrier::complete_tx::bytes; SASS UBLKCP).
+//
+// a7+a8 of SURVEY.md 8a: ElementRestriction::Mult + DiffusionIntegrator::AddMultPA +
+// ElementRestriction::MultTranspose (+ the essential-dof masks of ConstrainedOperator) in one kernel.
+//
+// Each CTA loops over batches of E consecutive elements (grid = resident CTAs x SMs).  One batch's q-data
+// is ONE contiguous 48 Q^3 E-byte block in HBM (layout [e][qz][c2][q2][2], see pa_kernels.cuh), so a single
+// elected thread moves it with one bulk copy; the copy for batch b' = b + gridDim.x is issued as soon as
+// the Z stage of batch b has consumed the buffer and lands while the CTA runs Yt(b), Xt(b), X(b'), Y(b').
+// The (padded) gather map of b' is double buffered the same way, and the x gathers of b' are issued one
+// stage ahead into registers.  No thread ever waits on a global load it has just issued, so the kernel does
+// not depend on occupancy to hide HBM latency (ncu of the non-pipelined kernel: 34 % long-scoreboard, 26 %
+// barrier stalls -- profiles/r01_apply_ncu.md).
+#pragma once
+#include "pa_kernels.cuh"
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int P, int E>
+struct TmaCfg : ApplyCfg<P, E> {
+    using B = ApplyCfg<P, E>;
+    static constexpr int D3 = B::D * B::D * B::D;
+    static constexpr int DP3 = (D3 + 3) & ~3;                       // gather-map row padded to 16 bytes
+    static constexpr int QE = 6 * B::Q * B::Q * B::Q;               // doubles of q-data per element
+    // byte offsets inside dynamic shared memory
+    static constexpr size_t OFF_Q = 0;                                                  // [E][QE] doubles (16B aligned)
+    static constexpr size_t OFF_IDX = OFF_Q + (size_t)E * QE * 8;                       // [2][E][DP3] ints
+    static constexpr size_t OFF_WORK = (OFF_IDX + (size_t)2 * E * DP3 * 4 + 15) & ~(size_t)15;
+    static constexpr size_t OFF_BAR = (OFF_WORK + (size_t)E * B::ES * 8 + 15) & ~(size_t)15;   // 3 mbarriers
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
+};
+
+template <int P, int E, bool DEN, int MINB>
+__global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
+pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
+                    double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status)
+{
+    using C = TmaCfg<P, E>;
+    constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
+    constexpr int DP3 = C::DP3, QE = C::QE;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (status != nullptr && *status != 0) return;
+    double *sq = reinterpret_cast<double *>(smem_raw + C::OFF_Q);
+    int *sidx = reinterpret_cast<int *>(smem_raw + C::OFF_IDX);
+    double *smem = reinterpret_cast<double *>(smem_raw + C::OFF_WORK);
+    uint64_t *bar_q = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
+    uint64_t *bar_i = bar_q + 1;      // two of them
+
+    const int tid = threadIdx.x;
+    const int nb = (ne + E - 1) / E;
+
+    const int ez = tid / LZ, q2 = tid - ez * LZ;
+    const int ex = tid / LX, lx = tid - ex * LX;
+    const int xdz = lx / D, xdy = lx - xdz * D;
+    const bool xrole = tid < E * LX;
+    const int ey = tid / LY, ly = tid - ey * LY;
+    const int ydz = ly / Q, yqx = ly - ydz * Q;
+    const bool yrole = tid < E * LY;
+
+    if (tid == 0) {
+        mbar_init(bar_q, 1); mbar_init(bar_i, 1); mbar_init(bar_i + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int b = blockIdx.x;
+    if (b >= nb) return;
+    auto batch_elems = [&](int bb) { return min(E, ne - bb * E); };
+    // ---- prologue: stage gather map and q-data of the first batch ----
+    if (tid == 0) {
+        const int n0 = batch_elems(b);
+        mbar_expect_tx(bar_i, (uint32_t)(n0 * DP3 * 4));
+        bulk_g2s(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i);
+        mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
+        bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+    }
+    double xs[D], xsn[D];
+    double part = 0.0;
+    mbar_wait(bar_i, 0);
+    if (xrole && b * E + ex < ne) {
+        const int *gi = sidx + ex * DP3 + lx * D;
+#pragma unroll
+        for (int i = 0; i < D; i++) { const int g = gi[i]; xs[i] = g >= 0 ? x[g] : 0.0; }
+    }
+
+    uint32_t it = 0;
+    for (; b < nb; b += gridDim.x, it++) {
+        const int e0 = b * E;
+        const int bn = b + gridDim.x;
+        const int e0n = bn * E;
+        const bool has_next = bn < nb;
+        const bool xvalid = xrole && (e0 + ex) < ne;
+        const bool yvalid = yrole && (e0 + ey) < ne;
+        const bool zvalid = (e0 + ez) < ne;
+        const bool xnext = xrole && has_next && (e0n + ex) < ne;
+        const int cur = it & 1, nxt = cur ^ 1;
+        // The basis tables are addressed through a loop-variant (always zero) offset: without it the compiler
+        // hoists all 60 B/G coefficients out of the batch loop, overflows the uniform register file and pays
+        // ~480 R2UR/MOV instructions per element shuffling them back (ncu source page, profiles/r01_apply_ncu.md).
+        const LpfBasisTab &T = c_tab[P + (it >> 30)];
+
+        // gather map of the next batch -> the other index buffer (last read two stages ago, before a barrier)
+        if (tid == 0 && has_next) {
+            const int n1 = batch_elems(bn);
+            fence_proxy_async();
+            mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
+            bulk_g2s(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt);
+        }
+
+        // ---- X stage ----
+        if (xvalid) {
+            double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                double sb = 0.0, sg = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; i++) { sb = fma(T.B[q * D + i], xs[i], sb); sg = fma(T.G[q * D + i], xs[i], sg); }
+                a[q] = sb;
+                a[C::SAA + q] = sg;
+            }
+        }
+        __syncthreads();
+
+        // ---- Y stage ----
+        if (yvalid) {
+            const double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
+            double ua[D], ub[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) { ua[i] = a[i * C::SAY]; ub[i] = a[C::SAA + i * C::SAY]; }
+            double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    s0 = fma(T.B[q * D + i], ua[i], s0);
+                    s1 = fma(T.G[q * D + i], ua[i], s1);
+                    s2 = fma(T.B[q * D + i], ub[i], s2);
+                }
+                bb[q * Q] = s0;
+                bb[C::SBA + q * Q] = s1;
+                bb[2 * C::SBA + q * Q] = s2;
+            }
+        }
+        __syncthreads();
+
+        // ---- Z stage: q-data from shared memory ----
+        mbar_wait(bar_q, it & 1);
+        if (zvalid) {
+            double *bb = smem + ez * C::ES + C::OFFB + q2;
+            const double2 *sqv = reinterpret_cast<const double2 *>(sq) + (size_t)ez * (QE / 2) + q2;
+            double ubb[D], ubg[D], ugb[D], cbb[D], cbg[D], cgb[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                ubb[i] = bb[i * C::SBZ]; ubg[i] = bb[C::SBA + i * C::SBZ]; ugb[i] = bb[2 * C::SBA + i * C::SBZ];
+                cbb[i] = 0.0; cbg[i] = 0.0; cgb[i] = 0.0;
+            }
+#pragma unroll
+            for (int qz = 0; qz < Q; qz++) {
+                const double2 d0 = sqv[(qz * 3 + 0) * LZ], d1 = sqv[(qz * 3 + 1) * LZ], d2 = sqv[(qz * 3 + 2) * LZ];
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    g0 = fma(T.B[qz * D + i], ugb[i], g0);
+                    g1 = fma(T.B[qz * D + i], ubg[i], g1);
+                    g2 = fma(T.G[qz * D + i], ubb[i], g2);
+                }
+                const double f0 = d0.x * g0 + d0.y * g1 + d1.x * g2;
+                const double f1 = d0.y * g0 + d1.y * g1 + d2.x * g2;
+                const double f2 = d1.x * g0 + d2.x * g1 + d2.y * g2;
+#pragma unroll
+                for (int i = 0; i < D; i++) {
+                    cgb[i] = fma(T.B[qz * D + i], f0, cgb[i]);
+                    cbg[i] = fma(T.B[qz * D + i], f1, cbg[i]);
+                    cbb[i] = fma(T.G[qz * D + i], f2, cbb[i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                bb[i * C::SBZ] = cbb[i]; bb[C::SBA + i * C::SBZ] = cbg[i]; bb[2 * C::SBA + i * C::SBZ] = cgb[i];
+            }
+        }
+        __syncthreads();
+
+        // the q buffer is free: stream the next batch's q-data into it while Yt, Xt, X', Y' run
+        if (tid == 0 && has_next) {
+            const int n1 = batch_elems(bn);
+            fence_proxy_async();
+            mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
+            bulk_g2s(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q);
+        }
+        // x gathers of the next batch (its gather map landed long ago)
+        if (has_next) mbar_wait(bar_i + nxt, ((it + 1) >> 1) & 1);
+        if (xnext) {
+            const int *gi = sidx + nxt * E * DP3 + ex * DP3 + lx * D;
+#pragma unroll
+            for (int i = 0; i < D; i++) { const int g = gi[i]; xsn[i] = g >= 0 ? x[g] : 0.0; }
+        }
+
+        // ---- Yt stage ----
+        if (yvalid) {
+            const double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
+            double vbb[Q], vbg[Q], vgb[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) { vbb[q] = bb[q * Q]; vbg[q] = bb[C::SBA + q * Q]; vgb[q] = bb[2 * C::SBA + q * Q]; }
+            double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double ta = 0.0, tb = 0.0;
+#pragma unroll
+                for (int q = 0; q < Q; q++) {
+                    ta = fma(T.B[q * D + i], vbb[q], ta);
+                    ta = fma(T.G[q * D + i], vbg[q], ta);
+                    tb = fma(T.B[q * D + i], vgb[q], tb);
+                }
+                a[i * C::SAY] = ta;
+                a[C::SAA + i * C::SAY] = tb;
+            }
+        }
+        __syncthreads();
+
+        // ---- Xt stage + scatter-add ----
+        if (xvalid) {
+            const double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
+            const int *gi = sidx + cur * E * DP3 + ex * DP3 + lx * D;
+            double ta[Q], tb[Q];
+#pragma unroll
+            for (int q = 0; q < Q; q++) { ta[q] = a[q]; tb[q] = a[C::SAA + q]; }
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                double s = 0.0;
+#pragma unroll
+                for (int q = 0; q < Q; q++) { s = fma(T.B[q * D + i], ta[q], s); s = fma(T.G[q * D + i], tb[q], s); }
+                const int g = gi[i];
+                if (g >= 0) {
+                    atomicAdd(y + g, s);
+                    if (DEN) part = fma(xs[i], s, part);
+                }
+            }
+        }
+        if (xnext) {
+#pragma unroll
+            for (int i = 0; i < D; i++) xs[i] = xsn[i];
+        }
+        __syncthreads();     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
+    }
+
+    if (DEN && den_slots != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __shared__ double wsum[32];
+        const int w = tid >> 5, nw = (C::NT + 31) >> 5;
+        if ((tid & 31) == 0) wsum[w] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < nw; i++) s += wsum[i];
+            atomicAdd(den_slots + (blockIdx.x & 255), s);
+        }
+    }
+}

@@ -49,6 +49,7 @@ struct ApplyCfg {
     static constexpr int D = P + 1, Q = P + 2;
     static constexpr int LX = D * D, LY = D * Q, LZ = Q * Q;
     static constexpr int NT = E * LZ;
+    static constexpr int DP3 = (D * D * D + 3) & ~3;    // gather-map row stride (rows padded to 16 bytes for bulk copies)
     // smem A: [arr 2][dz][dy][qx]; dy stride odd, dz stride == Q (mod 16) so that both the X-stage
     // stores (fixed qx, consecutive lines) and the Y-stage loads (fixed dy, consecutive (dz,qx)) spread
     // over the 16 eight-byte bank pairs.
@@ -111,7 +112,7 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
 #pragma unroll
             for (int i = 0; i < D; i++) { idx[i] = 0; xs[i] = src[i]; }
         } else {
-            const int *gi = gmap + (size_t)(e0 + ex) * D3 + lx * D;
+            const int *gi = gmap + (size_t)(e0 + ex) * C::DP3 + lx * D;
 #pragma unroll
             for (int i = 0; i < D; i++) idx[i] = gi[i];
 #pragma unroll
@@ -334,7 +335,7 @@ __global__ void pa_qdata_export_kernel(int p, int ne, const double *__restrict__
 __global__ void pa_diag_kernel(int p, int ne, const double *__restrict__ qd, const int *__restrict__ gmap,
                                double *__restrict__ diag)
 {
-    const int D = p + 1, Q = p + 2, Q2 = Q * Q, D3 = D * D * D;
+    const int D = p + 1, Q = p + 2, Q2 = Q * Q, D3 = D * D * D, DP3 = (D3 + 3) & ~3;
     const LpfBasisTab &T = c_tab[p];
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (size_t)ne * D3) return;
@@ -356,6 +357,6 @@ __global__ void pa_diag_kernel(int p, int ne, const double *__restrict__ qd, con
             }
         }
     }
-    const int g = gmap[gid];
+    const int g = gmap[(size_t)e * DP3 + d];
     atomicAdd(diag + (g >= 0 ? g : ~g), acc);
 }

@@ -239,13 +239,13 @@ __global__ void surface_dz_kernel(int p, int ns, const int *__restrict__ sd_off,
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ns) return;
-    const int D = p + 1, D3 = D * D * D;
+    const int D = p + 1, D3 = D * D * D, DP3 = (D3 + 3) & ~3;
     const LpfBasisTab &T = c_tab[p];
     double acc = 0.0;
     for (int j = sd_off[s]; j < sd_off[s + 1]; j++) {
         const int e = sd_elem[j], n = sd_node[j];
         const int k = n / (D * D), jj = (n / D) % D, i = n % D;
-        const int *g = gmap + (size_t)e * D3;
+        const int *g = gmap + (size_t)e * DP3;
         double g0 = 0.0, g1 = 0.0, g2 = 0.0;
         for (int m = 0; m < D; m++) {
             g0 = fma(T.Dhat[i * D + m], phi[g[m + D * (jj + D * k)]], g0);

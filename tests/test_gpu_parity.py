@@ -69,17 +69,34 @@ def test_qdata_apply_diag_all_orders(lpf, orc, cuda, tank, p):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
-def test_apply_kernel_variants_p4(lpf, orc, cuda, tank, variant):
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 10, 12, 14, 15, 20, 21, 22, 23, 24, 25, 26])
+def test_apply_kernel_variants_p4(lpf, orc, cuda, variant):
+    """Every compiled (elements-per-CTA, pipelining) variant of the order-4 kernel, on a mesh whose element
+    count (7x1x3 refined once = 168, perturbed) is ragged for every batch size and spans several batches
+    per CTA for the persistent kernels."""
     torch = cuda
+    tank = lpf.Mesh.wave_tank(7, 1, 3).refine(1).perturb(0.12)
     sp = lpf.Space(tank, 4)
     A = orc.PAOperator(oracle_space_from(orc, sp))
     ctx = _ctx(lpf, torch, sp)
     ctx.set_option("apply_variant", variant)
     x = orc.hash_noise(sp.ndof, seed=11)
     xd, yd = _dev(torch, x), torch.empty(sp.ndof, dtype=torch.float64, device="cuda")
-    ctx.apply_L(xd, yd)
-    assert rel_err(yd.cpu().numpy(), A.mult(x)) < TOL_OP
+    ref = A.mult(x)
+    for max_ctas in (0, 5, 1):          # persistent kernels: many batches per CTA, odd/even iteration counts
+        ctx.set_option("max_ctas", max_ctas)
+        ctx.apply_L(xd, yd)
+        assert rel_err(yd.cpu().numpy(), ref) < TOL_OP, (variant, max_ctas)
+    # PCG denominator path (x . A x accumulated in the kernel) through a short constrained solve
+    ctx.jacobi_setup()
+    b = _dev(torch, orc.hash_noise(sp.ndof, seed=12))
+    xs = torch.zeros_like(b)
+    info = ctx.pcg(b, xs, rel_tol=1e-10, max_iter=400)
+    ctx.set_option("apply_variant", 0); ctx.set_option("max_ctas", 0)
+    xs0 = torch.zeros_like(b)
+    info0 = ctx.pcg(b, xs0, rel_tol=1e-10, max_iter=400)
+    assert info.converged and abs(info.iterations - info0.iterations) <= 1
+    assert rel_err(xs.cpu().numpy(), xs0.cpu().numpy()) < 1e-8
     ctx.close()
 
 

@@ -173,54 +173,65 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
     return LPF_OK;
 }
 
-// variant 0 = default for the order; other values pick alternative (E, prefetch) pairs for tuning
+// Kernel selection.  L-vector applies (the hot path) use the persistent TMA-staged kernel; variant 0 is the
+// tuned default per order, variants 1..3 are alternative (elements per CTA, CTAs per SM) pairs kept for the
+// tuning sweep in bench.py, variants >= 100 select the earlier one-batch-per-CTA kernel (100 + E index) and
+// 200+ the register-pipelined one, so every design that profiles/ discusses stays measurable.
+// E-vector applies (AddMultPA adapter entry point) use the one-batch-per-CTA kernel.
+#define LPF_TMA(P, E, MINB) return apply_tma_launch_t<P, E, MINB>(c, gmap, x, y, den, status)
+#define LPF_OLD(P, E, PF) return apply_launch_t<P, E, PF, EVEC, 1>(c, gmap, x, y, den, status)
 template <bool EVEC>
 int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
 {
     const int v = c->variant;
-    switch (c->p) {
-        case 1: return apply_launch_t<1, 16, true, EVEC, 1>(c, gmap, x, y, den, status);
-        case 2: return apply_launch_t<2, 16, true, EVEC, 1>(c, gmap, x, y, den, status);
-        case 3: return v == 1 ? apply_launch_t<3, 4, true, EVEC, 1>(c, gmap, x, y, den, status)
-                              : apply_launch_t<3, 8, true, EVEC, 1>(c, gmap, x, y, den, status);
-        case 4:
-            if (!EVEC && v >= 20) {
-                if (v == 20) return apply_tma_launch_t<4, 2, 4>(c, gmap, x, y, den, status);
-                if (v == 21) return apply_tma_launch_t<4, 2, 5>(c, gmap, x, y, den, status);
-                if (v == 22) return apply_tma_launch_t<4, 3, 3>(c, gmap, x, y, den, status);
-                if (v == 23) return apply_tma_launch_t<4, 4, 2>(c, gmap, x, y, den, status);
-                if (v == 24) return apply_tma_launch_t<4, 8, 1>(c, gmap, x, y, den, status);
-                if (v == 25) return apply_tma_launch_t<4, 1, 6>(c, gmap, x, y, den, status);
-                if (v == 26) return apply_tma_launch_t<4, 2, 6>(c, gmap, x, y, den, status);
-                if (v == 27) return apply_tma_launch_t<4, 4, 3>(c, gmap, x, y, den, status);
-            }
-            if (!EVEC && v >= 10) {
-                if (v == 10) return apply_pipe_launch_t<4, 2, 4>(c, gmap, x, y, den, status);
-                if (v == 11) return apply_pipe_launch_t<4, 2, 5>(c, gmap, x, y, den, status);
-                if (v == 12) return apply_pipe_launch_t<4, 4, 2>(c, gmap, x, y, den, status);
-                if (v == 13) return apply_pipe_launch_t<4, 4, 3>(c, gmap, x, y, den, status);
-                if (v == 14) return apply_pipe_launch_t<4, 3, 3>(c, gmap, x, y, den, status);
-                if (v == 15) return apply_pipe_launch_t<4, 8, 1>(c, gmap, x, y, den, status);
-                if (v == 16) return apply_pipe_launch_t<4, 8, 2>(c, gmap, x, y, den, status);
-                if (v == 17) return apply_pipe_launch_t<4, 2, 6>(c, gmap, x, y, den, status);
-            }
-            if (v == 1) return apply_launch_t<4, 8, true, EVEC, 1>(c, gmap, x, y, den, status);
-            if (v == 2) return apply_launch_t<4, 4, false, EVEC, 1>(c, gmap, x, y, den, status);
-            if (v == 3) return apply_launch_t<4, 2, true, EVEC, 1>(c, gmap, x, y, den, status);
-            if (v == 4) return apply_launch_t<4, 8, false, EVEC, 1>(c, gmap, x, y, den, status);
-            if (v == 5) return apply_launch_t<4, 1, true, EVEC, 1>(c, gmap, x, y, den, status);
-            if (v == 6) return apply_launch_t<4, 3, true, EVEC, 1>(c, gmap, x, y, den, status);
-            if (v == 7) return apply_launch_t<4, 2, false, EVEC, 1>(c, gmap, x, y, den, status);
-            return apply_launch_t<4, 4, true, EVEC, 1>(c, gmap, x, y, den, status);
-        case 5: return v == 1 ? apply_launch_t<5, 2, true, EVEC, 1>(c, gmap, x, y, den, status)
-                              : apply_launch_t<5, 4, true, EVEC, 1>(c, gmap, x, y, den, status);
-        case 6: return v == 1 ? apply_launch_t<6, 2, true, EVEC, 1>(c, gmap, x, y, den, status)
-                              : apply_launch_t<6, 4, false, EVEC, 1>(c, gmap, x, y, den, status);
-        case 7: return apply_launch_t<7, 2, false, EVEC, 1>(c, gmap, x, y, den, status);
-        case 8: return apply_launch_t<8, 2, false, EVEC, 1>(c, gmap, x, y, den, status);
-        default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
+    if (EVEC || v >= 100) {
+        switch (c->p) {
+            case 1: LPF_OLD(1, 16, true);
+            case 2: LPF_OLD(2, 16, true);
+            case 3: if (v == 101) LPF_OLD(3, 4, true); LPF_OLD(3, 8, true);
+            case 4:
+                if (v == 101) LPF_OLD(4, 8, true);
+                if (v == 102) LPF_OLD(4, 4, false);
+                if (v == 103) LPF_OLD(4, 2, true);
+                if (v == 104) LPF_OLD(4, 3, true);
+                LPF_OLD(4, 4, true);
+            case 5: if (v == 101) LPF_OLD(5, 2, true); LPF_OLD(5, 4, true);
+            case 6: if (v == 101) LPF_OLD(6, 2, true); LPF_OLD(6, 4, false);
+            case 7: LPF_OLD(7, 2, false);
+            case 8: LPF_OLD(8, 2, false);
+            default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
+        }
     }
+    if constexpr (!EVEC) {
+        switch (c->p) {
+            case 1: if (v == 1) LPF_TMA(1, 8, 4); if (v == 2) LPF_TMA(1, 32, 2); LPF_TMA(1, 16, 3);
+            case 2: if (v == 1) LPF_TMA(2, 4, 5); if (v == 2) LPF_TMA(2, 16, 2); LPF_TMA(2, 8, 3);
+            case 3: if (v == 1) LPF_TMA(3, 3, 5); if (v == 2) LPF_TMA(3, 8, 2); LPF_TMA(3, 5, 3);
+            case 4:
+                if (v == 1) LPF_TMA(4, 2, 5);
+                if (v == 2) LPF_TMA(4, 4, 3);
+                if (v == 3) LPF_TMA(4, 8, 1);
+                if (v == 4) LPF_TMA(4, 4, 2);
+                if (v == 5) LPF_TMA(4, 2, 4);
+                if (v >= 10 && v < 20) {
+                    if (v == 10) return apply_pipe_launch_t<4, 2, 4>(c, gmap, x, y, den, status);
+                    if (v == 12) return apply_pipe_launch_t<4, 4, 2>(c, gmap, x, y, den, status);
+                    if (v == 14) return apply_pipe_launch_t<4, 3, 3>(c, gmap, x, y, den, status);
+                    return apply_pipe_launch_t<4, 8, 1>(c, gmap, x, y, den, status);
+                }
+                LPF_TMA(4, 3, 3);
+            case 5: if (v == 1) LPF_TMA(5, 3, 2); if (v == 2) LPF_TMA(5, 1, 4); LPF_TMA(5, 2, 3);
+            case 6: if (v == 1) LPF_TMA(6, 1, 3); if (v == 2) LPF_TMA(6, 3, 1); LPF_TMA(6, 2, 2);
+            case 7: if (v == 1) LPF_TMA(7, 1, 2); LPF_TMA(7, 2, 1);
+            case 8: if (v == 1) LPF_TMA(8, 1, 2); LPF_TMA(8, 2, 1);
+            default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
+        }
+    }
+    return LPF_ERR_UNSUPPORTED;
 }
+#undef LPF_TMA
+#undef LPF_OLD
+
 
 int halo_sum(lpf_ctx *c, lpf::HaloPlan &h, double *v)
 {

@@ -52,6 +52,10 @@ def test_qdata_apply_diag_all_orders(lpf, orc, cuda, tank, p):
     assert rel_err(y, A.mult(x)) < TOL_OP
     if fa is not None:
         assert rel_err(y, fa.mult(x)) < TOL_OP         # against the full-assembly twin as well
+    ctx.set_option("max_ctas", 1)                      # one persistent CTA walks all batches
+    ctx.apply_L(xd, yd)
+    assert rel_err(yd.cpu().numpy(), A.mult(x)) < TOL_OP
+    ctx.set_option("max_ctas", 0)
     # E-vector entry point: AddMultPA semantics (accumulates)
     xE = _dev(torch, x[sp.gather])
     yE = torch.ones_like(xE)
@@ -69,7 +73,26 @@ def test_qdata_apply_diag_all_orders(lpf, orc, cuda, tank, p):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 10, 12, 14, 15, 20, 21, 22, 23, 24, 25, 26])
+@pytest.mark.parametrize("p,variant", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (5, 1), (5, 2), (6, 1), (6, 2), (7, 1), (8, 1)])
+def test_apply_kernel_alternative_variants(lpf, orc, cuda, p, variant):
+    """The non-default (elements per CTA, CTAs per SM) instantiations of the persistent kernel, forced through
+    several batches per CTA."""
+    torch = cuda
+    sp = lpf.Space(lpf.Mesh.wave_tank(5, 1, 3).perturb(0.12) if p >= 5 else lpf.Mesh.wave_tank(7, 1, 3).refine(1).perturb(0.12), p)
+    A = orc.PAOperator(oracle_space_from(orc, sp))
+    ctx = _ctx(lpf, torch, sp)
+    ctx.set_option("apply_variant", variant)
+    x = orc.hash_noise(sp.ndof, seed=11)
+    xd, yd = _dev(torch, x), torch.empty(sp.ndof, dtype=torch.float64, device="cuda")
+    ref = A.mult(x)
+    for max_ctas in (0, 3, 1):
+        ctx.set_option("max_ctas", max_ctas)
+        ctx.apply_L(xd, yd)
+        assert rel_err(yd.cpu().numpy(), ref) < TOL_OP, (p, variant, max_ctas)
+    ctx.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 12, 14, 15, 100, 101, 102, 103, 104])
 def test_apply_kernel_variants_p4(lpf, orc, cuda, variant):
     """Every compiled (elements-per-CTA, pipelining) variant of the order-4 kernel, on a mesh whose element
     count (7x1x3 refined once = 168, perturbed) is ragged for every batch size and spans several batches

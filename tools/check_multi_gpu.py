@@ -1,0 +1,134 @@
+"""Multi-GPU parity check (one process per GPU, NCCL halo-sum): run under torchrun on N GPUs of one node.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tools/check_multi_gpu.py [--order 4] [--mesh tank|cylinder]
+
+Every rank builds its x-slab (RCB) partition, runs the constrained operator, a Laplace solve and three RK4
+steps through the C-ABI, and the results are compared with the single-GPU run of the same library on rank 0's
+device (which tests/ pins against the oracle): operator 1e-12, potentials / elevations 1e-10, CG iterations
+within +-1; copies of shared dofs must be bit-identical across ranks.
+"""
+import argparse
+import importlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--mesh", default="tank")
+    a = ap.parse_args()
+    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    torch.cuda.set_stream(torch.cuda.Stream())
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream().cuda_stream
+    if a.mesh == "tank":
+        mesh = lpf.Mesh.wave_tank(32, 2, 8).perturb(0.1)
+    else:
+        mesh = lpf.Mesh.read(os.path.join(ROOT, "tests", "meshes", "cylinder_half.mesh"))
+    p = a.order
+    sp = lpf.Space(mesh, p, nranks=world, rank=rank)
+    ctx = lpf.Context(sp, device=local, stream=stream)
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    ctx.comm_init(idt.cpu().numpy().tobytes())
+    ctx.pa_setup()
+    ctx.jacobi_setup()
+
+    # serial twin on this rank's GPU (every rank builds it: cheap at this size, and no gather of inputs needed)
+    ssp = lpf.Space(mesh, p)
+    sctx = lpf.Context(ssp, device=local, stream=stream)
+    sctx.pa_setup()
+    sctx.jacobi_setup()
+    l2g = torch.from_numpy(sp.l2g.astype(np.int64)).cuda()
+    fails = []
+
+    def check(name, val, tol):
+        ok = val < tol
+        t = torch.tensor([0.0 if ok else 1.0], device="cuda")
+        dist.all_reduce(t)
+        if rank == 0:
+            print(f"  {name:34s} {val:.3e}  (tol {tol:g})  {'ok' if float(t[0]) == 0 else 'FAIL'}", flush=True)
+        if float(t[0]) != 0:
+            fails.append(name)
+
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    xg = torch.rand(ssp.ndof, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    yg = torch.empty_like(xg)
+    sctx.apply_T(xg, yg)
+    xl = xg[l2g].contiguous()
+    yl = torch.empty_like(xl)
+    ctx.apply_T(xl, yl)
+    check("constrained apply (halo-sum)", rel(yl.cpu().numpy(), yg[l2g].cpu().numpy()), 1e-12)
+    dg, dl = torch.empty_like(xg), torch.empty_like(xl)
+    sctx.diag(dg); ctx.diag(dl)
+    check("diagonal", rel(dl.cpu().numpy(), dg[l2g].cpu().numpy()), 1e-12)
+    # shared copies bit-identical: sum over ranks of (value * owned) scattered to global == every copy
+    glob = torch.zeros(ssp.ndof, dtype=torch.float64, device="cuda")
+    glob[l2g] = yl * torch.from_numpy(sp.owned.astype(np.float64)).cuda()
+    dist.all_reduce(glob)
+    check("shared copies bit-identical", float((glob[l2g] - yl).abs().max()), 1e-300)
+
+    # Laplace solve from Airy Dirichlet data
+    w = lpf.wave_params()
+    xyz = ssp.node_coordinates()
+    lo, hi = mesh.bounding_box()
+    ex = -0.5 * w["H"] * w["cwave"] * np.cosh(w["k"] * (xyz[:, 2] - lo[2])) / np.sinh(w["kh"]) * np.sin(-w["k"] * xyz[:, 0])
+    phi0 = np.zeros(ssp.ndof); phi0[ssp.ess] = ex[ssp.ess]
+    pg = torch.from_numpy(phi0).cuda()
+    pl = pg[l2g].contiguous()
+    si = sctx.laplace_solve(pg, rel_tol=1e-12, max_iter=2000)
+    mi = ctx.laplace_solve(pl, rel_tol=1e-12, max_iter=2000)
+    check("laplace solve potential", rel(pl.cpu().numpy(), pg[l2g].cpu().numpy()), 1e-10)
+    check("CG iterations |multi - single|", abs(mi.iterations - si.iterations), 1.5)
+    if rank == 0:
+        print(f"    iterations: single {si.iterations}, {world} GPUs {mi.iterations}", flush=True)
+
+    # three RK4 steps of the ss.cpp RHS
+    prm = lpf.make_rhs_params(w, rel_tol=1e-12, max_iter=2000)
+    sctx.rhs_setup(prm); ctx.rhs_setup(prm)
+    ph = -w["k"] * ssp.surf_xy[:, 0]
+    st = np.concatenate([0.5 * w["H"] * np.cos(ph), -0.5 * w["H"] * w["cwave"] / np.tanh(w["kh"]) * np.sin(ph)])
+    sg = torch.from_numpy(st).cuda()
+    sg_idx = torch.from_numpy(sp.surf_g.astype(np.int64)).cuda()
+    ns_g, ns_l = ssp.nsurf, sp.nsurf
+    sl = torch.cat([sg[:ns_g][sg_idx], sg[ns_g:][sg_idx]]).contiguous()
+    dt = w["T"] / 60
+    tg = tl = 0.0
+    for _ in range(3):
+        tg = sctx.rk4_step(sg, tg, dt)
+        tl = ctx.rk4_step(sl, tl, dt)
+    if ns_l:
+        check("eta after 3 RK4 steps", rel(sl[:ns_l].cpu().numpy(), sg[:ns_g][sg_idx].cpu().numpy()), 1e-10)
+        check("phi_fs after 3 RK4 steps", rel(sl[ns_l:].cpu().numpy(), sg[ns_g:][sg_idx].cpu().numpy()), 1e-10)
+    else:
+        check("eta after 3 RK4 steps", 0.0, 1e-10); check("phi_fs after 3 RK4 steps", 0.0, 1e-10)
+    its_s = [i.iterations for i in sctx.last_solve_info()]
+    its_m = [i.iterations for i in ctx.last_solve_info()]
+    check("RK4 stage CG iterations", max(abs(x - y) for x, y in zip(its_s, its_m)), 1.5)
+    if rank == 0:
+        print(f"    stage iterations: single {its_s}, {world} GPUs {its_m}")
+        print("MULTI-GPU PARITY: " + ("OK" if not fails else "FAILED " + str(fails)), flush=True)
+    ctx.close(); sctx.close()
+    dist.destroy_process_group()
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -79,6 +79,8 @@ typedef struct {
     int ndof;                  /* local L-dofs */
     const double *corners;     /* [ne][8][3] trilinear corners (lexicographic) or NULL if `jac` given */
     const double *jac;         /* optional GeometricFactors::J layout [Q^3][3][3][ne] (q fastest) */
+    const double *jinv_z;      /* optional [ne][D^3][3]: third column of J^-1 at the element nodes (GetDerivative
+                                  geometry); required for the surface RHS when `corners` is NULL */
     const int *gather;         /* [ne][D^3] element dof -> L-dof */
     int n_ess;
     const int *ess;            /* essential L-dofs */

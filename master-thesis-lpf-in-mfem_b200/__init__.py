@@ -39,7 +39,7 @@ c_u8p = C.POINTER(C.c_uint8)
 class SpaceDesc(C.Structure):
     _fields_ = [
         ("order", C.c_int), ("ne", C.c_int), ("ndof", C.c_int),
-        ("corners", c_dp), ("jac", c_dp), ("gather", c_ip),
+        ("corners", c_dp), ("jac", c_dp), ("jinv_z", c_dp), ("gather", c_ip),
         ("n_ess", C.c_int), ("ess", c_ip),
         ("n_surf", C.c_int), ("surf2vol", c_ip), ("surf_xy", c_dp),
         ("n_surf_elems", C.c_int), ("surf_elems", c_ip), ("surf_mult", c_ip),
@@ -250,7 +250,7 @@ class Space:
         self.n_surf_global = d.n_surf_global
 
     @classmethod
-    def from_arrays(cls, order, corners, gather, ess, surf2vol=None, surf_xy=None):
+    def from_arrays(cls, order, corners, gather, ess, surf2vol=None, surf_xy=None, jac=None, jinv_z=None):
         """Serial space from plain arrays -- the route an MFEM adapter takes (gather map from
         ElementRestriction, geometry, ess_tdof_list; include/lpf_b200.h lpf_space_desc)."""
         self = cls.__new__(cls)
@@ -283,6 +283,15 @@ class Space:
         d.surf_mult = self.surf_mult.ctypes.data_as(c_ip)
         d.nranks, d.rank = 1, 0
         d.n_true_global, d.n_surf_global = self.ndof, self.nsurf
+        if jac is not None:
+            # MFEM GeometricFactors::J layout [Q^3][3][3][ne] (+ nodal J^-1 column for GetDerivative): the
+            # kernels then never look at `corners`
+            self.jac = np.ascontiguousarray(jac, dtype=np.float64)
+            self.jinv_z = np.ascontiguousarray(jinv_z, dtype=np.float64) if jinv_z is not None else None
+            d.jac = self.jac.ctypes.data_as(c_dp)
+            d.corners = None
+            if self.jinv_z is not None:
+                d.jinv_z = self.jinv_z.ctypes.data_as(c_dp)
         self.desc = d
         return self
 

@@ -71,7 +71,7 @@ struct lpf_ctx {
     int max_ctas = 0;
     int ess_general = 0;      // lpf_pcg: search directions may be non-zero on essential dofs
     // geometry / maps
-    double *corners = nullptr, *jac = nullptr, *qd = nullptr;
+    double *corners = nullptr, *jac = nullptr, *jinv_z = nullptr, *qd = nullptr;
     int *gmap = nullptr, *gmap_c = nullptr, *ess = nullptr;
     uint8_t *essmask = nullptr, *owned = nullptr, *surf_owned = nullptr;
     // solver vectors
@@ -287,6 +287,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         LpfBasisTab t;
         std::memset(&t, 0, sizeof(t));
         std::copy(bs.B.begin(), bs.B.end(), t.B);
+        for (size_t i = 0; i < bs.B.size(); i++) { t.BG[2 * i] = bs.B[i]; t.BG[2 * i + 1] = bs.G[i]; }
         std::copy(bs.G.begin(), bs.G.end(), t.G);
         std::copy(bs.Dhat.begin(), bs.Dhat.end(), t.Dhat);
         std::copy(bs.nodes.begin(), bs.nodes.end(), t.nodes);
@@ -296,6 +297,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     }
     if (d->corners) LPF_TRY(upload(c->corners, d->corners, (size_t)c->ne * 24, &c->bytes));
     if (d->jac) LPF_TRY(upload(c->jac, d->jac, (size_t)c->ne * Q3 * 9, &c->bytes));
+    if (d->jinv_z) LPF_TRY(upload(c->jinv_z, d->jinv_z, (size_t)c->ne * D3 * 3, &c->bytes));
     const int DP3 = (D3 + 3) & ~3;       // rows padded to 16 bytes (bulk-copy granularity)
     {
         std::vector<int> gp((size_t)c->ne * DP3, 0);
@@ -414,7 +416,7 @@ void lpf_destroy(lpf_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->pcg_graph) cudaGraphExecDestroy(c->pcg_graph);
     c->comm.destroy();
-    void *ptrs[] = {c->corners, c->jac, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
+    void *ptrs[] = {c->corners, c->jac, c->jinv_z, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
                     c->z, c->d, c->ad, c->X, c->Bv, c->tmp, c->den_slots, c->partials, c->st, c->bad, c->surf2vol,
                     c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->wsum, c->rk_k,
                     c->rk_y, c->rk_z, c->state_dev};
@@ -765,7 +767,7 @@ int lpf_surface_dz(lpf_ctx *c, const double *phi, double *wt)
     if (!c || !phi || !wt) { lpf::set_error("lpf_surface_dz: null argument"); return LPF_ERR_ARG; }
     if (c->nsurf == 0) return LPF_OK;
     const int ns = c->nsurf;
-    surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, phi, c->wsum);
+    surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, c->jinv_z, phi, c->wsum);
     c->launches++;
     LPF_TRY(halo_sum(c, c->shalo, c->wsum));
     surface_div_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(ns, c->surf_mult, c->wsum, wt);
@@ -777,7 +779,7 @@ int lpf_surface_dz(lpf_ctx *c, const double *phi, double *wt)
 int lpf_rhs_setup(lpf_ctx *c, const lpf_rhs_params *p, const double *cgen, const double *cabs)
 {
     if (!c || !p) { lpf::set_error("lpf_rhs_setup: null argument"); return LPF_ERR_ARG; }
-    if (!c->corners) { lpf::set_error("lpf_rhs_setup: surface derivative needs the corner geometry"); return LPF_ERR_STATE; }
+    if (!c->corners && !c->jinv_z) { lpf::set_error("lpf_rhs_setup: surface derivative needs `corners` or `jinv_z` in the descriptor"); return LPF_ERR_STATE; }
     if (p->use_relaxation && (!cgen || !cabs || !(p->tau > 0.0))) { lpf::set_error("lpf_rhs_setup: relaxation needs cgen, cabs and tau > 0"); return LPF_ERR_ARG; }
     c->rhs.g = p->g; c->rhs.H = p->H; c->rhs.omega = p->omega; c->rhs.k = p->k; c->rhs.kx = p->kx_dir; c->rhs.ky = p->ky_dir;
     c->rhs.cwave = p->cwave; c->rhs.coth_kh = std::cosh(p->kh) / std::sinh(p->kh); c->rhs.T = p->T;
@@ -803,7 +805,7 @@ static int rhs_impl(lpf_ctx *c, double t, const double *state, double *dstate, l
     }
     LPF_TRY(solve_from_X(c, c->rel_tol, c->abs_tol, c->max_iter, info));
     if (ns) {
-        surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, c->X, c->wsum);
+        surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, c->jinv_z, c->X, c->wsum);
         c->launches++;
         LPF_TRY(halo_sum(c, c->shalo, c->wsum));
         surface_rhs_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(ns, c->rhs, t, c->surf_mult, c->wsum, state, c->surf_xy, c->cgen, c->cabs, dstate);

@@ -128,6 +128,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
         // hoists all 60 B/G coefficients out of the batch loop, overflows the uniform register file and pays
         // ~480 R2UR/MOV instructions per element shuffling them back (ncu source page, profiles/r01_apply_ncu.md).
         const LpfBasisTab &T = c_tab[P + (it >> 30)];
+#define BGL(q, i) (reinterpret_cast<const double2 *>(T.BG)[(q) * D + (i)])     /* {B, G}[q][i]: one LDCU.128 */
 
         // gather map of the next batch -> the other index buffer (last read two stages ago, before a barrier)
         if (tid == 0 && has_next) {
@@ -144,7 +145,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
             for (int q = 0; q < Q; q++) {
                 double sb = 0.0, sg = 0.0;
 #pragma unroll
-                for (int i = 0; i < D; i++) { sb = fma(T.B[q * D + i], xs[i], sb); sg = fma(T.G[q * D + i], xs[i], sg); }
+                for (int i = 0; i < D; i++) { const double2 c = BGL(q, i); sb = fma(c.x, xs[i], sb); sg = fma(c.y, xs[i], sg); }
                 a[q] = sb;
                 a[C::SAA + q] = sg;
             }
@@ -163,9 +164,10 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
                 double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
                 for (int i = 0; i < D; i++) {
-                    s0 = fma(T.B[q * D + i], ua[i], s0);
-                    s1 = fma(T.G[q * D + i], ua[i], s1);
-                    s2 = fma(T.B[q * D + i], ub[i], s2);
+                    const double2 c = BGL(q, i);
+                    s0 = fma(c.x, ua[i], s0);
+                    s1 = fma(c.y, ua[i], s1);
+                    s2 = fma(c.x, ub[i], s2);
                 }
                 bb[q * Q] = s0;
                 bb[C::SBA + q * Q] = s1;
@@ -191,18 +193,20 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
                 double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
                 for (int i = 0; i < D; i++) {
-                    g0 = fma(T.B[qz * D + i], ugb[i], g0);
-                    g1 = fma(T.B[qz * D + i], ubg[i], g1);
-                    g2 = fma(T.G[qz * D + i], ubb[i], g2);
+                    const double2 c = BGL(qz, i);
+                    g0 = fma(c.x, ugb[i], g0);
+                    g1 = fma(c.x, ubg[i], g1);
+                    g2 = fma(c.y, ubb[i], g2);
                 }
                 const double f0 = d0.x * g0 + d0.y * g1 + d1.x * g2;
                 const double f1 = d0.y * g0 + d1.y * g1 + d2.x * g2;
                 const double f2 = d1.x * g0 + d2.x * g1 + d2.y * g2;
 #pragma unroll
                 for (int i = 0; i < D; i++) {
-                    cgb[i] = fma(T.B[qz * D + i], f0, cgb[i]);
-                    cbg[i] = fma(T.B[qz * D + i], f1, cbg[i]);
-                    cbb[i] = fma(T.G[qz * D + i], f2, cbb[i]);
+                    const double2 c = BGL(qz, i);
+                    cgb[i] = fma(c.x, f0, cgb[i]);
+                    cbg[i] = fma(c.x, f1, cbg[i]);
+                    cbb[i] = fma(c.y, f2, cbb[i]);
                 }
             }
 #pragma unroll
@@ -239,9 +243,10 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
                 double ta = 0.0, tb = 0.0;
 #pragma unroll
                 for (int q = 0; q < Q; q++) {
-                    ta = fma(T.B[q * D + i], vbb[q], ta);
-                    ta = fma(T.G[q * D + i], vbg[q], ta);
-                    tb = fma(T.B[q * D + i], vgb[q], tb);
+                    const double2 c = BGL(q, i);
+                    ta = fma(c.x, vbb[q], ta);
+                    ta = fma(c.y, vbg[q], ta);
+                    tb = fma(c.x, vgb[q], tb);
                 }
                 a[i * C::SAY] = ta;
                 a[C::SAA + i * C::SAY] = tb;
@@ -260,7 +265,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
             for (int i = 0; i < D; i++) {
                 double s = 0.0;
 #pragma unroll
-                for (int q = 0; q < Q; q++) { s = fma(T.B[q * D + i], ta[q], s); s = fma(T.G[q * D + i], tb[q], s); }
+                for (int q = 0; q < Q; q++) { const double2 c = BGL(q, i); s = fma(c.x, ta[q], s); s = fma(c.y, tb[q], s); }
                 const int g = gi[i];
                 if (g >= 0) {
                     atomicAdd(y + g, s);
@@ -273,6 +278,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
             for (int i = 0; i < D; i++) xs[i] = xsn[i];
         }
         __syncthreads();     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
+#undef BGL
     }
 
     if (DEN && den_slots != nullptr) {

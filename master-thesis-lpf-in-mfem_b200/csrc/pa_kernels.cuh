@@ -25,7 +25,10 @@
 
 #define LPF_MAXP 8
 
-struct LpfBasisTab {
+struct __align__(16) LpfBasisTab {
+    // {B, G} interleaved per (q, d): one 16-byte uniform load (LDCU.128) feeds both FMAs that every stage
+    // issues on the same (q, d) pair -- halves the coefficient loads of the apply kernels
+    double BG[2 * (LPF_MAXP + 2) * (LPF_MAXP + 1)];
     double B[(LPF_MAXP + 2) * (LPF_MAXP + 1)];     // [Q][D]
     double G[(LPF_MAXP + 2) * (LPF_MAXP + 1)];
     double Dhat[(LPF_MAXP + 1) * (LPF_MAXP + 1)];  // [D][D]
@@ -123,7 +126,7 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
         for (int q = 0; q < Q; q++) {
             double sb = 0.0, sg = 0.0;
 #pragma unroll
-            for (int i = 0; i < D; i++) { sb = fma(T.B[q * D + i], xs[i], sb); sg = fma(T.G[q * D + i], xs[i], sg); }
+            for (int i = 0; i < D; i++) { sb = fma(T.BG[2 * (q * D + i)], xs[i], sb); sg = fma(T.BG[2 * (q * D + i) + 1], xs[i], sg); }
             a[q] = sb;
             a[C::SAA + q] = sg;
         }
@@ -145,9 +148,9 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int i = 0; i < D; i++) {
-                s0 = fma(T.B[q * D + i], ua[i], s0);     // B_y B_x u
-                s1 = fma(T.G[q * D + i], ua[i], s1);     // G_y B_x u
-                s2 = fma(T.B[q * D + i], ub[i], s2);     // B_y G_x u
+                s0 = fma(T.BG[2 * (q * D + i)], ua[i], s0);     // B_y B_x u
+                s1 = fma(T.BG[2 * (q * D + i) + 1], ua[i], s1);     // G_y B_x u
+                s2 = fma(T.BG[2 * (q * D + i)], ub[i], s2);     // B_y G_x u
             }
             b[q * Q] = s0;
             b[C::SBA + q * Q] = s1;
@@ -170,9 +173,9 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
             double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
             for (int i = 0; i < D; i++) {
-                g0 = fma(T.B[qz * D + i], ugb[i], g0);
-                g1 = fma(T.B[qz * D + i], ubg[i], g1);
-                g2 = fma(T.G[qz * D + i], ubb[i], g2);
+                g0 = fma(T.BG[2 * (qz * D + i)], ugb[i], g0);
+                g1 = fma(T.BG[2 * (qz * D + i)], ubg[i], g1);
+                g2 = fma(T.BG[2 * (qz * D + i) + 1], ubb[i], g2);
             }
             double2 d0, d1, d2;
             if (PREFETCH) { d0 = qv[qz][0]; d1 = qv[qz][1]; d2 = qv[qz][2]; }
@@ -187,9 +190,9 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
             const double f2 = d1.x * g0 + d2.x * g1 + d2.y * g2;
 #pragma unroll
             for (int i = 0; i < D; i++) {
-                cgb[i] = fma(T.B[qz * D + i], f0, cgb[i]);
-                cbg[i] = fma(T.B[qz * D + i], f1, cbg[i]);
-                cbb[i] = fma(T.G[qz * D + i], f2, cbb[i]);
+                cgb[i] = fma(T.BG[2 * (qz * D + i)], f0, cgb[i]);
+                cbg[i] = fma(T.BG[2 * (qz * D + i)], f1, cbg[i]);
+                cbb[i] = fma(T.BG[2 * (qz * D + i) + 1], f2, cbb[i]);
             }
         }
 #pragma unroll
@@ -211,9 +214,9 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
             double ta = 0.0, tb = 0.0;
 #pragma unroll
             for (int q = 0; q < Q; q++) {
-                ta = fma(T.B[q * D + i], vbb[q], ta);
-                ta = fma(T.G[q * D + i], vbg[q], ta);
-                tb = fma(T.B[q * D + i], vgb[q], tb);
+                ta = fma(T.BG[2 * (q * D + i)], vbb[q], ta);
+                ta = fma(T.BG[2 * (q * D + i) + 1], vbg[q], ta);
+                tb = fma(T.BG[2 * (q * D + i)], vgb[q], tb);
             }
             a[i * C::SAY] = ta;
             a[C::SAA + i * C::SAY] = tb;
@@ -233,7 +236,7 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
         for (int i = 0; i < D; i++) {
             double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < Q; q++) { s = fma(T.B[q * D + i], ta[q], s); s = fma(T.G[q * D + i], tb[q], s); }
+            for (int q = 0; q < Q; q++) { s = fma(T.BG[2 * (q * D + i)], ta[q], s); s = fma(T.BG[2 * (q * D + i) + 1], tb[q], s); }
             if (EVEC) dst[i] += s;
             else if (idx[i] >= 0) { atomicAdd(y + idx[i], s); part = fma(xs[i], s, part); }
         }

@@ -234,8 +234,8 @@ __global__ void halo_unpack_kernel(int n, const int *__restrict__ shared, const 
 // One thread per surface dof walks its (element, local node) list in a fixed order: deterministic.
 __global__ void surface_dz_kernel(int p, int ns, const int *__restrict__ sd_off, const int *__restrict__ sd_elem,
                                   const int *__restrict__ sd_node, const int *__restrict__ gmap,
-                                  const double *__restrict__ corners, const double *__restrict__ phi,
-                                  double *__restrict__ wsum)
+                                  const double *__restrict__ corners, const double *__restrict__ jinv_z,
+                                  const double *__restrict__ phi, double *__restrict__ wsum)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ns) return;
@@ -252,13 +252,19 @@ __global__ void surface_dz_kernel(int p, int ns, const int *__restrict__ sd_off,
             g1 = fma(T.Dhat[jj * D + m], phi[g[i + D * (m + D * k)]], g1);
             g2 = fma(T.Dhat[k * D + m], phi[g[i + D * (jj + D * m)]], g2);
         }
-        double J[3][3];
-        trilinear_jac(corners + (size_t)e * 24, T.nodes[i], T.nodes[jj], T.nodes[k], J);
-        const double det = J[0][0] * (J[1][1] * J[2][2] - J[2][1] * J[1][2]) - J[1][0] * (J[0][1] * J[2][2] - J[2][1] * J[0][2])
-                         + J[2][0] * (J[0][1] * J[1][2] - J[1][1] * J[0][2]);
-        const double i0 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-        const double i1 = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-        const double i2 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        double i0, i1, i2;
+        if (jinv_z != nullptr) {
+            const double *ji = jinv_z + ((size_t)e * D3 + n) * 3;
+            i0 = ji[0]; i1 = ji[1]; i2 = ji[2];
+        } else {
+            double J[3][3];
+            trilinear_jac(corners + (size_t)e * 24, T.nodes[i], T.nodes[jj], T.nodes[k], J);
+            const double det = J[0][0] * (J[1][1] * J[2][2] - J[2][1] * J[1][2]) - J[1][0] * (J[0][1] * J[2][2] - J[2][1] * J[0][2])
+                             + J[2][0] * (J[0][1] * J[1][2] - J[1][1] * J[0][2]);
+            i0 = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+            i1 = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+            i2 = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        }
         acc += i0 * g0 + i1 * g1 + i2 * g2;
     }
     wsum[s] = acc;

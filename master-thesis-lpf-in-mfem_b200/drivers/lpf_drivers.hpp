@@ -1,0 +1,176 @@
+// Host-side C++ layer of the drivers: thin RAII classes over the C-ABI (include/lpf_b200.h) named after
+// the MFEM objects the reference drivers use, so that drivers/*.cpp read like Solvers/*.cpp and
+// Convergence_and_Scaling/*.cpp of the reference.  One std::thread per GPU stands in for one MPI rank.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "lpf_b200.h"
+
+namespace lpfd {
+
+inline void check(int rc, const char *what)
+{
+    if (rc != LPF_OK) throw std::runtime_error(std::string(what) + ": " + lpf_last_error());
+}
+
+// ---- command line: --key value pairs with defaults equal to the reference's source constants ----
+struct Args {
+    int argc; char **argv;
+    const char *get(const char *key, const char *def) const
+    {
+        for (int i = 1; i + 1 < argc; i++) if (std::strcmp(argv[i], key) == 0) return argv[i + 1];
+        return def;
+    }
+    int geti(const char *key, int def) const { return std::atoi(get(key, std::to_string(def).c_str())); }
+    double getd(const char *key, double def) const { const char *v = get(key, nullptr); return v ? std::atof(v) : def; }
+    bool has(const char *key) const { for (int i = 1; i < argc; i++) if (std::strcmp(argv[i], key) == 0) return true; return false; }
+};
+
+// ---- mfem::Mesh ----
+class Mesh {
+public:
+    explicit Mesh(const std::string &file) : h_(lpf_mesh_read(file.c_str())) { if (!h_) throw std::runtime_error(lpf_last_error()); }
+    Mesh(int nx, int ny, int nz, double Lx, double Ly, double H, bool periodic_x)
+        : h_(lpf_mesh_make_wave_tank(nx, ny, nz, Lx, Ly, H, periodic_x)) { if (!h_) throw std::runtime_error(lpf_last_error()); }
+    ~Mesh() { lpf_mesh_destroy(h_); }
+    Mesh(const Mesh &) = delete;
+    void UniformRefinement() { check(lpf_mesh_refine(h_, 1), "UniformRefinement"); }
+    void GetBoundingBox(double lo[3], double hi[3]) const { check(lpf_mesh_bounding_box(h_, lo, hi), "GetBoundingBox"); }
+    int GetNE() const { return lpf_mesh_num_elements(h_); }
+    lpf_mesh *handle() const { return h_; }
+    /// "wave-tank.mesh" style names map onto the generator (the reference's mesh files are its outputs)
+    static Mesh *FromName(const std::string &name)
+    {
+        const double H = 1.0 / (2.0 * M_PI);
+        if (name == "wave-tank.mesh") return new Mesh(3, 1, 1, 1.0, 0.1, H, true);
+        if (name == "wave-tank-big.mesh") return new Mesh(32, 2, 8, 1.0, 0.1, H, true);
+        if (name == "wave-tank-big2.mesh") return new Mesh(64, 2, 8, 1.0, 0.1, H, true);
+        if (name == "wave-tank-big4.mesh") return new Mesh(64, 2, 16, 1.0, 0.1, H, true);
+        if (name == "wave-tank-big8.mesh") return new Mesh(128, 2, 16, 1.0, 0.1, H, true);
+        if (name == "wave-tank-finite.mesh") return new Mesh(36, 1, 1, 12.0, 1.0, H, false);
+        return new Mesh(name);
+    }
+private:
+    lpf_mesh *h_;
+};
+
+// ---- H1 ParFiniteElementSpace of one rank + its device context (what rhs_linear owns) ----
+class RankSpace {
+public:
+    RankSpace(const Mesh &mesh, int order, int nranks, int rank)
+        : s_(lpf_space_create(mesh.handle(), order, 2, nranks, rank))
+    {
+        if (!s_) throw std::runtime_error(lpf_last_error());
+        check(lpf_space_desc_get(s_, &desc), "lpf_space_desc_get");
+    }
+    ~RankSpace() { lpf_space_destroy(s_); }
+    RankSpace(const RankSpace &) = delete;
+    int GetTrueVSize() const { int n = 0; for (int i = 0; i < desc.ndof; i++) n += desc.owned ? desc.owned[i] : 1; return n; }
+    long GlobalTrueVSize() const { return desc.n_true_global; }
+    std::vector<double> NodeCoordinates() const
+    {
+        std::vector<double> xyz((size_t)desc.ndof * 3);
+        check(lpf_space_node_coordinates(s_, xyz.data()), "node coordinates");
+        return xyz;
+    }
+    lpf_space_desc desc{};
+private:
+    lpf_space *s_;
+};
+
+// ---- wave parameters (lambda-mode, PF_linear_par_partial.cpp:298-306) ----
+struct Wave {
+    double H = 0.01, g = 9.81, lambda = 1.0, kh = 1.0, theta = 0.0;
+    double k, cwave, T, omega, kx_dir, ky_dir;
+    Wave() { finish(); }
+    void finish()
+    {
+        k = 2.0 * M_PI / lambda;
+        cwave = std::sqrt((g / k) * std::tanh(kh));
+        T = lambda / cwave;
+        omega = 2.0 * M_PI / T;
+        kx_dir = std::cos(theta); ky_dir = std::sin(theta);
+    }
+    double phase(double t, double x, double y) const { return omega * t - k * (kx_dir * x + ky_dir * y); }
+    double eta(double t, double x, double y) const { return 0.5 * H * std::cos(phase(t, x, y)); }
+    double phi_fs(double t, double x, double y) const { return -0.5 * H * cwave * std::cosh(kh) / std::sinh(kh) * std::sin(phase(t, x, y)); }
+    // volume potential with z measured from the bottom (laplace_solver.cpp:70-81)
+    double phi(double t, double x, double y, double zb) const { return -0.5 * H * cwave * std::cosh(k * zb) / std::sinh(kh) * std::sin(phase(t, x, y)); }
+    double w_surface(double t, double x, double y) const { return -0.5 * H * cwave * k * std::sin(phase(t, x, y)); }
+    lpf_rhs_params params(double tau, bool relax, double rel_tol, int max_iter) const
+    {
+        lpf_rhs_params p{};
+        p.g = g; p.H = H; p.omega = omega; p.k = k; p.kx_dir = kx_dir; p.ky_dir = ky_dir; p.cwave = cwave; p.kh = kh; p.T = T;
+        p.tau = tau; p.n_ramp = 3.0; p.use_relaxation = relax; p.rel_tol = rel_tol; p.abs_tol = 0.0; p.max_iter = max_iter;
+        return p;
+    }
+};
+
+// ---- rhs_linear : TimeDependentOperator + RK4Solver, device resident ----
+class RhsLinear {
+public:
+    RhsLinear(const RankSpace &sp, int device, const void *nccl_id) : ns_(sp.desc.n_surf), ndof_(sp.desc.ndof)
+    {
+        ctx_ = lpf_create(&sp.desc, device, nullptr);
+        if (!ctx_) throw std::runtime_error(std::string("lpf_create: ") + lpf_last_error());
+        if (sp.desc.nranks > 1) check(lpf_comm_init(ctx_, nccl_id), "lpf_comm_init");
+        check(lpf_pa_setup(ctx_), "a_loc_cach->Assemble()");           // PF_linear_par_partial.cpp:118-121
+        check(lpf_jacobi_setup(ctx_), "OperatorJacobiSmoother");        // :124
+        state_ = (double *)lpf_dev_alloc(sizeof(double) * 2 * (ns_ ? ns_ : 1));
+        if (!state_) throw std::runtime_error(lpf_last_error());
+    }
+    ~RhsLinear() { lpf_dev_free(state_); lpf_destroy(ctx_); }
+    RhsLinear(const RhsLinear &) = delete;
+    void Setup(const lpf_rhs_params &p, const double *cgen, const double *cabs) { check(lpf_rhs_setup(ctx_, &p, cgen, cabs), "lpf_rhs_setup"); }
+    void SetState(const std::vector<double> &s) { if (ns_) check(lpf_memcpy_h2d(state_, s.data(), sizeof(double) * 2 * ns_), "h2d"); }
+    void GetState(std::vector<double> &s) { s.resize(2 * (size_t)ns_); check(lpf_sync(ctx_), "sync"); if (ns_) check(lpf_memcpy_d2h(s.data(), state_, sizeof(double) * 2 * ns_), "d2h"); }
+    void Step(double &t, double dt) { check(lpf_rk4_step(ctx_, state_, &t, dt), "ode_solver->Step"); }   // :494
+    void Sync() { check(lpf_sync(ctx_), "sync"); }
+    std::vector<int> LastIterations()
+    {
+        lpf_pcg_info info[4]; int n = 0;
+        check(lpf_last_solve_info(ctx_, info, &n), "info");
+        std::vector<int> it; for (int i = 0; i < n; i++) it.push_back(info[i].iterations);
+        return it;
+    }
+    lpf_ctx *ctx() const { return ctx_; }
+    int nsurf() const { return ns_; }
+    int ndof() const { return ndof_; }
+private:
+    lpf_ctx *ctx_ = nullptr;
+    double *state_ = nullptr;
+    int ns_, ndof_;
+};
+
+// ---- one std::thread per GPU ("mpirun -np N") ----
+struct World {
+    int nranks;
+    unsigned char nccl_id[128];
+    std::vector<double> reduce_buf;
+    explicit World(int n) : nranks(n), reduce_buf(n, 0.0)
+    {
+        if (n > 1) check(lpf_comm_unique_id(nccl_id), "lpf_comm_unique_id");
+        const int ndev = lpf_device_count();
+        if (ndev < n) throw std::runtime_error("need " + std::to_string(n) + " GPUs, found " + std::to_string(ndev));
+    }
+    void run(const std::function<void(int)> &fn)
+    {
+        std::vector<std::thread> th;
+        std::vector<std::string> err(nranks);
+        for (int r = 0; r < nranks; r++)
+            th.emplace_back([&, r] { try { fn(r); } catch (const std::exception &e) { err[r] = e.what(); } });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < nranks; r++) if (!err[r].empty()) throw std::runtime_error("rank " + std::to_string(r) + ": " + err[r]);
+    }
+};
+
+}  // namespace lpfd

@@ -123,6 +123,7 @@ int lpf_space_desc_get(const lpf_space *s, lpf_space_desc *d)
     d->ndof = (int)p.l2g.size();
     d->corners = p.corners.data();
     d->jac = nullptr;
+    d->jinv_z = nullptr;
     d->gather = p.gather.data();
     d->n_ess = (int)p.ess.size();
     d->ess = p.ess.data();

@@ -334,6 +334,36 @@ def test_golden_vectors(lpf, cuda):
     ctx.close()
 
 
+def test_mfem_adapter_descriptor_route(lpf, orc, cuda, tank):
+    """The route include/lpf_mfem_adapter.hpp takes: geometry as a Jacobian array in MFEM's
+    GeometricFactors::J layout [Q^3][3][3][ne] plus nodal J^-1 columns, no corner coordinates."""
+    torch = cuda
+    p = 3
+    sp0 = lpf.Space(tank, p)
+    osp = oracle_space_from(orc, sp0)
+    bs = osp.basis
+    J = orc.jacobians_trilinear(osp.mesh.corners, bs.qpts)                  # [e, q, c, k]
+    jac = np.ascontiguousarray(np.transpose(J, (0, 3, 2, 1)))               # [e][k][c][q]  == J[q + Q3*(c + 3*(k + 3e))]
+    Jn = orc.jacobians_trilinear(osp.mesh.corners, bs.nodes)
+    jinv_z = np.ascontiguousarray(np.linalg.inv(Jn)[:, :, :, 2])            # [e][n][k]: Jinv(k, z)
+    sp = lpf.Space.from_arrays(p, sp0.corners, sp0.gather, sp0.ess, sp0.surf2vol, sp0.surf_xy, jac=jac, jinv_z=jinv_z)
+    ctx = _ctx(lpf, torch, sp)
+    ctx.jacobi_setup()
+    A = orc.PAOperator(osp)
+    x = orc.hash_noise(sp.ndof)
+    xd, yd = _dev(torch, x), torch.empty(sp.ndof, dtype=torch.float64, device="cuda")
+    ctx.apply_T(xd, yd)
+    assert rel_err(yd.cpu().numpy(), orc.ConstrainedOperator(A, osp.ess).mult(x)) < TOL_OP
+    wv, st0 = _initial_state(orc, sp0)
+    dt = wv.T / 40
+    ctx.rhs_setup(lpf.make_rhs_params(lpf.wave_params(), rel_tol=1e-12, max_iter=1000))
+    sd = _dev(torch, st0)
+    ctx.rk4_step(sd, 0.0, dt)
+    so, _ = orc.rk4_step(orc.RhsLinear(osp, wv, rel_tol=1e-12, max_iter=1000, operator=A), st0.copy(), 0.0, dt)
+    assert rel_err(sd.cpu().numpy(), so) < TOL_SOL
+    ctx.close()
+
+
 def test_full_size_properties_big8(lpf, cuda):
     """wave-tank-big8 (4096 hexes, 299 520 dofs at p=4; BASELINE config 3) and one refinement of it:
     size-independent checks -- symmetry, null space, positivity, E-vector vs L-vector consistency,

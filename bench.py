@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-rk4", action="store_true", help="skip the PCG-per-RK-step measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rk4-refine", type=int, default=1)
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: own NVLink peer-memory exchange or NCCL send/recv + all-reduce")
     return ap.parse_args()
 
 
@@ -164,7 +165,9 @@ def run_ours(a):
     stream = torch.cuda.current_stream().cuda_stream
     ctx = lpf.Context(sp, device=local, stream=stream)
     ctx.set_option("apply_variant", a.variant)
-    if world > 1:
+    if world > 1 and a.comm == "p2p":
+        ctx.p2p_connect(dist)
+    elif world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
@@ -247,11 +250,11 @@ def run_ours(a):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "hexes_per_gpu": sp.ne, "dofs_global": ndof_global, "order": p,
                    "l2_policy": "inputs larger than L2 (q-data %.2f GB per GPU), no flush" % (sp.ne * 48 * (p + 2) ** 3 / 1e9),
-                   "parallelism": f"x-slab domain decomposition x{world}, NCCL halo-sum" if world > 1 else "single GPU",
+                   "parallelism": (f"x-slab domain decomposition x{world}, halo-sum over " + ("NVLink peer memory (own kernels)" if a.comm == "p2p" else "NCCL send/recv")) if world > 1 else "single GPU",
                    "apply_variant": a.variant},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(p), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                     "kernel_ms": ms_kernel, "kernel": "pa_apply_kernel"},
+                     "kernel_ms": ms_kernel, "kernel": "pa_apply_tma_kernel"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "steps": e2e_steps, "api": "lpf_apply_T_host (pinned host x -> device -> apply -> host y)"},
         "gpu_launches": int(launches),

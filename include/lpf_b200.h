@@ -135,6 +135,15 @@ int lpf_nsurf(const lpf_ctx *ctx);
  * inside ParFiniteElementSpace::GroupComm() and CGSolver(MPI_COMM_WORLD) (:157). */
 int lpf_comm_unique_id(void *id128);
 int lpf_comm_init(lpf_ctx *ctx, const void *id128);
+/* Peer-memory exchange over NVLink (csrc/p2p.cuh): halo-sums and the PCG's scalar all-reduces are done by our
+ * own kernels with stores into the neighbours' mailboxes -- no NCCL call inside the solver, a few us per
+ * exchange.  Every rank exports its mailbox (64-byte CUDA IPC handle; raw pointer + device for ranks that are
+ * threads of ONE process), the host gathers the nranks handles (MPI_Allgather / torch.distributed), then every
+ * rank connects.  Once connected the context no longer needs lpf_comm_init.  Ranks <= 16, one node. */
+int lpf_p2p_export(lpf_ctx *ctx, void *handle64, uint64_t *raw_ptr, int *device);
+int lpf_p2p_connect(lpf_ctx *ctx, const void *handles /* [nranks][64] */, const uint64_t *raw_ptrs /* [nranks] */,
+                    const int *devices /* [nranks] */, int same_process);
+int lpf_p2p_error(lpf_ctx *ctx);                              /* 1 if a bounded flag wait timed out */
 
 /* a1  ParBilinearForm::Assemble (PARTIAL) -> DiffusionIntegrator::AssemblePA         (:118-121) */
 int lpf_pa_setup(lpf_ctx *ctx);

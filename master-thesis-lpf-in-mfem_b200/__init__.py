@@ -99,6 +99,9 @@ SIGNATURES = {
     "lpf_nsurf": (C.c_int, [_VP]),
     "lpf_comm_unique_id": (C.c_int, [_VP]),
     "lpf_comm_init": (C.c_int, [_VP, _VP]),
+    "lpf_p2p_export": (C.c_int, [_VP, _VP, C.POINTER(C.c_uint64), c_ip]),
+    "lpf_p2p_connect": (C.c_int, [_VP, _VP, C.POINTER(C.c_uint64), c_ip, C.c_int]),
+    "lpf_p2p_error": (C.c_int, [_VP]),
     "lpf_pa_setup": (C.c_int, [_VP]),
     "lpf_pa_qdata": (C.c_int, [_VP, _VP]),
     "lpf_pa_apply_E": (C.c_int, [_VP, _VP, _VP]),
@@ -342,6 +345,25 @@ class Context:
     def comm_init(self, id128: bytes):
         buf = C.create_string_buffer(id128, 128)
         _check(lib.lpf_comm_init(self.h, buf), "lpf_comm_init")
+
+    def p2p_connect(self, dist=None):
+        """Peer-memory exchange between the ranks of a torch.distributed job (one process per GPU): gathers the
+        64-byte CUDA IPC handles of all mailboxes and connects.  After this no NCCL call is made by the solver."""
+        import torch
+        if dist is None:
+            import torch.distributed as dist
+        h = C.create_string_buffer(64)
+        _check(lib.lpf_p2p_export(self.h, h, None, None), "lpf_p2p_export")
+        mine = torch.frombuffer(bytearray(h.raw), dtype=torch.uint8).cuda()
+        world = dist.get_world_size()
+        allh = [torch.zeros(64, dtype=torch.uint8, device="cuda") for _ in range(world)]
+        dist.all_gather(allh, mine)
+        buf = b"".join(t.cpu().numpy().tobytes() for t in allh)
+        _check(lib.lpf_p2p_connect(self.h, C.create_string_buffer(buf, len(buf)), None, None, 0), "lpf_p2p_connect")
+        dist.barrier()
+
+    def p2p_error(self):
+        return lib.lpf_p2p_error(self.h)
 
     def pa_setup(self):
         _check(lib.lpf_pa_setup(self.h), "lpf_pa_setup")

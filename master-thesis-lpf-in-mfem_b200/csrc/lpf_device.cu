@@ -16,6 +16,7 @@
 #include "pa_apply_pipe.cuh"
 #include "pa_apply_tma.cuh"
 #include "vec_kernels.cuh"
+#include "p2p.cuh"
 
 #define CUDA_TRY(call)                                                                              \
     do {                                                                                            \
@@ -93,6 +94,18 @@ struct lpf_ctx {
     // halo (multi-GPU)
     lpf::Comm comm;
     lpf::HaloPlan halo, shalo;
+    // peer-memory exchange (p2p.cuh); when connected it replaces every NCCL call of the solver
+    bool p2p_on = false;
+    P2PBox *box = nullptr;
+    size_t box_bytes = 0;
+    P2PLocal *p2p_local = nullptr;
+    P2PBox **peers_dev = nullptr;
+    std::vector<P2PBox *> peers;
+    std::vector<char> peer_opened;
+    P2PPlanDev p2p_plan[2]{};
+    int *p2p_send_nbr[2] = {nullptr, nullptr};
+    double **p2p_dst[2] = {nullptr, nullptr};
+    P2PDev p2p{};
     // host staging for *_host entry points
     double *hx = nullptr, *hy = nullptr;
     // CUDA graph of one PCG chunk
@@ -236,7 +249,17 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
 int halo_sum(lpf_ctx *c, lpf::HaloPlan &h, double *v)
 {
     if (c->nranks == 1 || h.n_nbr == 0) return LPF_OK;
-    if (!c->comm.ready()) { lpf::set_error("multi-rank context used before lpf_comm_init"); return LPF_ERR_STATE; }
+    if (c->p2p_on) {
+        const int plan = (&h == &c->halo) ? 0 : 1;
+        const P2PPlanDev &pd = c->p2p_plan[plan];
+        const int gp = std::max(1, std::min((h.total + 255) / 256, 64)), gu = std::max(1, std::min((h.n_shared + 255) / 256, 64));
+        p2p_pack_kernel<<<gp, 256, 0, c->stream>>>(c->p2p, pd, plan, v);
+        p2p_unpack_kernel<<<gu, 256, 0, c->stream>>>(c->p2p, pd, plan, v);
+        c->launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        return LPF_OK;
+    }
+    if (!c->comm.ready()) { lpf::set_error("multi-rank context used before lpf_comm_init / lpf_p2p_connect"); return LPF_ERR_STATE; }
     const int ns = h.total;
     halo_pack_kernel<<<(ns + 255) / 256, 256, 0, c->stream>>>(ns, h.send_dofs, v, h.sendbuf);
     c->launches++;
@@ -262,6 +285,90 @@ int upload_halo(lpf::HaloPlan &h, int n_nbr, const int *nbr_rank, const int *nbr
     LPF_TRY(upload(h.red_src, red_src, (size_t)red_off[n_shared], bytes));
     LPF_TRY(upload(h.sendbuf, (const double *)nullptr, (size_t)h.total, bytes));
     LPF_TRY(upload(h.recvbuf, (const double *)nullptr, (size_t)h.total, bytes));
+    return LPF_OK;
+}
+
+// Mailbox of this rank: header + double-buffered receive areas of both halo plans (see p2p.cuh)
+int p2p_create(lpf_ctx *c)
+{
+    const size_t hdr = (sizeof(P2PBox) + 255) & ~(size_t)255;
+    const size_t n0 = (size_t)c->halo.total, n1 = (size_t)c->shalo.total;
+    c->box_bytes = hdr + 2 * (n0 + n1) * sizeof(double) + 256;
+    CUDA_TRY(cudaMalloc((void **)&c->box, c->box_bytes));
+    CUDA_TRY(cudaMemset(c->box, 0, c->box_bytes));
+    P2PBox h;
+    std::memset(&h, 0, sizeof(h));
+    h.recv_byte_off[0][0] = (long long)hdr;
+    h.recv_byte_off[0][1] = (long long)(hdr + n0 * 8);
+    h.recv_byte_off[1][0] = (long long)(hdr + 2 * n0 * 8);
+    h.recv_byte_off[1][1] = (long long)(hdr + 2 * n0 * 8 + n1 * 8);
+    for (int k = 0; k < c->halo.n_nbr; k++) h.off_for_src[0][c->halo.nbr_rank[k]] = c->halo.nbr_offset[k];
+    for (int k = 0; k < c->shalo.n_nbr; k++) h.off_for_src[1][c->shalo.nbr_rank[k]] = c->shalo.nbr_offset[k];
+    CUDA_TRY(cudaMemcpy(c->box, &h, sizeof(h), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void **)&c->p2p_local, sizeof(P2PLocal)));
+    CUDA_TRY(cudaMemset(c->p2p_local, 0, sizeof(P2PLocal)));
+    c->bytes += c->box_bytes;
+    return LPF_OK;
+}
+
+int p2p_connect_impl(lpf_ctx *c, const void *handles, const uint64_t *raws, const int *devices, int same_process)
+{
+    const int R = c->nranks;
+    c->peers.assign(R, nullptr);
+    c->peer_opened.assign(R, 0);
+    for (int r = 0; r < R; r++) {
+        if (r == c->rank) { c->peers[r] = c->box; continue; }
+        if (same_process) {
+            if (!raws || !devices) { lpf::set_error("lpf_p2p_connect: same_process needs raw pointers and devices"); return LPF_ERR_ARG; }
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, c->dev, devices[r]));
+            if (!can) { lpf::set_error("lpf_p2p_connect: no peer access between the GPUs"); return LPF_ERR_COMM; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[r], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CUDA_TRY(e);
+            cudaGetLastError();
+            c->peers[r] = (P2PBox *)(uintptr_t)raws[r];
+        } else {
+            cudaIpcMemHandle_t mh;
+            std::memcpy(&mh, (const char *)handles + (size_t)r * sizeof(mh), sizeof(mh));
+            void *p = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+            c->peers[r] = (P2PBox *)p;
+            c->peer_opened[r] = 1;
+        }
+    }
+    CUDA_TRY(cudaMalloc((void **)&c->peers_dev, sizeof(P2PBox *) * R));
+    CUDA_TRY(cudaMemcpy(c->peers_dev, c->peers.data(), sizeof(P2PBox *) * R, cudaMemcpyHostToDevice));
+    lpf::HaloPlan *plans[2] = {&c->halo, &c->shalo};
+    for (int pl = 0; pl < 2; pl++) {
+        lpf::HaloPlan &h = *plans[pl];
+        P2PPlanDev &pd = c->p2p_plan[pl];
+        pd.n_nbr = h.n_nbr; pd.total = h.total; pd.n_shared = h.n_shared;
+        if (h.n_nbr == 0) continue;
+        std::vector<int> send_nbr(h.total);
+        for (int k = 0; k < h.n_nbr; k++) for (int i = h.nbr_offset[k]; i < h.nbr_offset[k + 1]; i++) send_nbr[i] = k;
+        std::vector<double *> dst(2 * (size_t)h.n_nbr);
+        for (int k = 0; k < h.n_nbr; k++) {
+            const int s = h.nbr_rank[k];
+            P2PBox ph;      // the neighbour's header tells where this rank writes inside its receive area
+            CUDA_TRY(cudaMemcpy(&ph, c->peers[s], sizeof(ph), cudaMemcpyDefault));
+            for (int par = 0; par < 2; par++)
+                dst[(size_t)par * h.n_nbr + k] = (double *)((char *)c->peers[s] + ph.recv_byte_off[pl][par]) + ph.off_for_src[pl][c->rank];
+        }
+        int *nr = nullptr, *no = nullptr;
+        LPF_TRY(upload(c->p2p_send_nbr[pl], send_nbr.data(), send_nbr.size(), &c->bytes));
+        LPF_TRY(upload(c->p2p_dst[pl], dst.data(), dst.size(), &c->bytes));
+        LPF_TRY(upload(nr, h.nbr_rank.data(), h.nbr_rank.size(), &c->bytes));
+        LPF_TRY(upload(no, h.nbr_offset.data(), h.nbr_offset.size(), &c->bytes));
+        pd.nbr_rank = nr; pd.nbr_offset = no;          // small tables, freed with the context's device at exit
+        pd.send_dofs = h.send_dofs; pd.send_nbr = c->p2p_send_nbr[pl]; pd.dst = c->p2p_dst[pl];
+        pd.shared = h.shared; pd.red_off = h.red_off; pd.red_src = h.red_src;
+        P2PBox mine;
+        CUDA_TRY(cudaMemcpy(&mine, c->box, sizeof(mine), cudaMemcpyDeviceToHost));
+        for (int par = 0; par < 2; par++) pd.recv[par] = (const double *)((char *)c->box + mine.recv_byte_off[pl][par]);
+    }
+    c->p2p.nranks = R; c->p2p.rank = c->rank; c->p2p.peers = c->peers_dev; c->p2p.mine = c->box; c->p2p.local = c->p2p_local;
+    c->p2p_on = true;
+    if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
     return LPF_OK;
 }
 
@@ -344,6 +451,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
                             d->red_off, d->red_src, &c->bytes));
         LPF_TRY(upload_halo(c->shalo, d->s_n_nbr, d->s_nbr_rank, d->s_nbr_offset, d->s_send, d->s_n_shared, d->s_shared,
                             d->s_red_off, d->s_red_src, &c->bytes));
+        if (c->nranks <= LPF_P2P_MAXR) LPF_TRY(p2p_create(c));
     }
     // surface tables
     if (c->nsurf > 0) {
@@ -422,6 +530,9 @@ void lpf_destroy(lpf_ctx *c)
                     c->rk_y, c->rk_z, c->state_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     free_halo(c->halo); free_halo(c->shalo);
+    for (size_t r = 0; r < c->peers.size(); r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
+    void *pp[] = {c->box, c->p2p_local, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1], c->p2p_dst[0], c->p2p_dst[1]};
+    for (void *p : pp) if (p) cudaFree(p);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->state_pinned) cudaFreeHost(c->state_pinned);
     if (c->hx) cudaFreeHost(c->hx);
@@ -464,6 +575,36 @@ int lpf_comm_init(lpf_ctx *c, const void *id128)
     if (!c || !id128) { lpf::set_error("lpf_comm_init: null argument"); return LPF_ERR_ARG; }
     CUDA_TRY(cudaSetDevice(c->dev));
     return c->comm.init(id128, c->nranks, c->rank);
+}
+
+int lpf_p2p_export(lpf_ctx *c, void *handle64, uint64_t *raw_ptr, int *device)
+{
+    if (!c || !handle64) { lpf::set_error("lpf_p2p_export: null argument"); return LPF_ERR_ARG; }
+    if (!c->box) { lpf::set_error("lpf_p2p_export: single-rank context (or more than 16 ranks) has no mailbox"); return LPF_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(c->dev));
+    cudaIpcMemHandle_t mh;
+    static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    CUDA_TRY(cudaIpcGetMemHandle(&mh, c->box));
+    std::memcpy(handle64, &mh, sizeof(mh));
+    if (raw_ptr) *raw_ptr = (uint64_t)(uintptr_t)c->box;
+    if (device) *device = c->dev;
+    return LPF_OK;
+}
+
+int lpf_p2p_connect(lpf_ctx *c, const void *handles, const uint64_t *raw_ptrs, const int *devices, int same_process)
+{
+    if (!c || (!handles && !same_process)) { lpf::set_error("lpf_p2p_connect: null argument"); return LPF_ERR_ARG; }
+    if (!c->box) { lpf::set_error("lpf_p2p_connect: context has no mailbox"); return LPF_ERR_STATE; }
+    CUDA_TRY(cudaSetDevice(c->dev));
+    return p2p_connect_impl(c, handles, raw_ptrs, devices, same_process);
+}
+
+int lpf_p2p_error(lpf_ctx *c)
+{
+    if (!c || !c->p2p_on) return 0;
+    int e = 0;
+    if (cudaMemcpy(&e, &c->p2p_local->error, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return e;
 }
 
 // ---- a1 -------------------------------------------------------------------------------------------
@@ -591,6 +732,29 @@ int ess_fix(lpf_ctx *c)
     return LPF_OK;
 }
 
+// cross-rank sum of a PCG scalar and what follows it (mode = P2P_RED_NOM / _BETA / _DEN)
+int multi_reduce(lpf_ctx *c, int mode)
+{
+    if (c->p2p_on) {
+        p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(c->p2p, &c->st->red[0], mode, c->st, c->den_slots);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+        return LPF_OK;
+    }
+    if (!c->comm.ready()) { lpf::set_error("multi-rank context used before lpf_comm_init / lpf_p2p_connect"); return LPF_ERR_STATE; }
+    if (mode == P2P_RED_DEN) {
+        pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
+        c->launches++;
+        return c->comm.allreduce_sum(&c->st->red[1], 1, c->stream);
+    }
+    LPF_TRY(c->comm.allreduce_sum(&c->st->red[0], 1, c->stream));
+    if (mode == P2P_RED_NOM) pcg_fin_nom_kernel<<<1, 1, 0, c->stream>>>(c->st);
+    else pcg_fin_beta_kernel<<<1, 1, 0, c->stream>>>(c->st);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
 // one CG iteration body: update (+ dot), direction, apply (+ den); all skip themselves once status != 0
 int pcg_iteration(lpf_ctx *c)
 {
@@ -599,9 +763,7 @@ int pcg_iteration(lpf_ctx *c)
     if (multi) {
         pcg_update_kernel<true><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->den_slots, c->partials);
         c->launches++;
-        LPF_TRY(c->comm.allreduce_sum(&c->st->red[0], 1, c->stream));
-        pcg_fin_beta_kernel<<<1, 1, 0, c->stream>>>(c->st);
-        c->launches++;
+        LPF_TRY(multi_reduce(c, P2P_RED_BETA));
     } else {
         pcg_update_kernel<false><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, nullptr, c->st, c->den_slots, c->partials);
         c->launches++;
@@ -612,9 +774,7 @@ int pcg_iteration(lpf_ctx *c)
     LPF_TRY(ess_fix(c));
     if (multi) {
         LPF_TRY(halo_sum(c, c->halo, c->ad));
-        pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
-        c->launches++;
-        LPF_TRY(c->comm.allreduce_sum(&c->st->red[1], 1, c->stream));
+        LPF_TRY(multi_reduce(c, P2P_RED_DEN));
     }
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
@@ -673,9 +833,7 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
     if (multi) {
         pcg_init_kernel<true><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
-        LPF_TRY(c->comm.allreduce_sum(&c->st->red[0], 1, c->stream));
-        pcg_fin_nom_kernel<<<1, 1, 0, c->stream>>>(c->st);
-        c->launches++;
+        LPF_TRY(multi_reduce(c, P2P_RED_NOM));
     } else {
         pcg_init_kernel<false><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, nullptr, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
@@ -684,9 +842,7 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
     LPF_TRY(ess_fix(c));
     if (multi) {
         LPF_TRY(halo_sum(c, c->halo, c->ad));
-        pcg_den_local_kernel<<<1, LPF_DEN_SLOTS, 0, c->stream>>>(c->st, c->den_slots);
-        c->launches++;
-        LPF_TRY(c->comm.allreduce_sum(&c->st->red[1], 1, c->stream));
+        LPF_TRY(multi_reduce(c, P2P_RED_DEN));
     }
     CUDA_TRY(cudaGetLastError());
     // iterate in chunks; the only host round trip is the status poll after each chunk

@@ -36,7 +36,7 @@ int main(int argc, char *argv[])
                hi[0] - lo[0], w.lambda, w.kh, w.k, w.cwave, w.T, w.omega, w.H);
         printf("%g\nRunning on %d GPUs\nStarting time integration with %d steps\n", dt, num_procs, nsteps);
 
-        World world(num_procs);
+        World world(num_procs, std::string(a.get("--comm", "p2p")) == "nccl");
         std::mutex io;
         double eta_max_global = 0.0;
         world.run([&](int myid) {
@@ -63,7 +63,7 @@ int main(int argc, char *argv[])
                 }
                 cgen[s] = cg; cabs[s] = ca;
             }
-            RhsLinear surface(fespace, myid, world.nccl_id);
+            RhsLinear surface(fespace, myid, world);
             surface.Setup(w.params(dt, relax, 1e-12, cyl ? 2000 : 1000), cgen.data(), cabs.data());   // :157-164, tau = dt :470
             surface.SetState(state);
             std::vector<double> env(ns, -1e300);

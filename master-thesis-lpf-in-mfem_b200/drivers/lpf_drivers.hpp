@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <cstdint>
 #include <functional>
+#include <mutex>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -115,14 +118,63 @@ struct Wave {
     }
 };
 
+// ---- one std::thread per GPU ("mpirun -np N") ----
+class ThreadBarrier {
+public:
+    explicit ThreadBarrier(int n) : n_(n) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        const int gen = gen_;
+        if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen != gen_; });
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+};
+
+struct World {
+    int nranks;
+    bool use_nccl;                     // --comm nccl: NCCL send/recv + all-reduce instead of the peer-memory exchange
+    unsigned char nccl_id[128];
+    std::vector<uint64_t> raw_ptrs;    // mailboxes of all ranks (threads of one process share the address space)
+    std::vector<int> devices;
+    ThreadBarrier barrier;
+    explicit World(int n, bool nccl = false) : nranks(n), use_nccl(nccl), raw_ptrs(n, 0), devices(n, 0), barrier(n)
+    {
+        if (n > 1 && use_nccl) check(lpf_comm_unique_id(nccl_id), "lpf_comm_unique_id");
+        const int ndev = lpf_device_count();
+        if (ndev < n) throw std::runtime_error("need " + std::to_string(n) + " GPUs, found " + std::to_string(ndev));
+    }
+    void run(const std::function<void(int)> &fn)
+    {
+        std::vector<std::thread> th;
+        std::vector<std::string> err(nranks);
+        for (int r = 0; r < nranks; r++)
+            th.emplace_back([&, r] { try { fn(r); } catch (const std::exception &e) { err[r] = e.what(); fprintf(stderr, "rank %d: %s\n", r, e.what()); if (nranks > 1) std::abort(); } });
+        for (auto &t : th) t.join();
+        for (int r = 0; r < nranks; r++) if (!err[r].empty()) throw std::runtime_error("rank " + std::to_string(r) + ": " + err[r]);
+    }
+};
+
 // ---- rhs_linear : TimeDependentOperator + RK4Solver, device resident ----
 class RhsLinear {
 public:
-    RhsLinear(const RankSpace &sp, int device, const void *nccl_id) : ns_(sp.desc.n_surf), ndof_(sp.desc.ndof)
+    RhsLinear(const RankSpace &sp, int device, World &world) : ns_(sp.desc.n_surf), ndof_(sp.desc.ndof)
     {
         ctx_ = lpf_create(&sp.desc, device, nullptr);
         if (!ctx_) throw std::runtime_error(std::string("lpf_create: ") + lpf_last_error());
-        if (sp.desc.nranks > 1) check(lpf_comm_init(ctx_, nccl_id), "lpf_comm_init");
+        if (sp.desc.nranks > 1 && world.use_nccl) check(lpf_comm_init(ctx_, world.nccl_id), "lpf_comm_init");
+        else if (sp.desc.nranks > 1) {
+            // replaces MPI_COMM_WORLD inside CGSolver / GroupCommunicator: peer-memory mailboxes over NVLink
+            unsigned char h[64];
+            check(lpf_p2p_export(ctx_, h, &world.raw_ptrs[sp.desc.rank], &world.devices[sp.desc.rank]), "lpf_p2p_export");
+            world.barrier.wait();
+            check(lpf_p2p_connect(ctx_, nullptr, world.raw_ptrs.data(), world.devices.data(), 1), "lpf_p2p_connect");
+            world.barrier.wait();
+        }
         check(lpf_pa_setup(ctx_), "a_loc_cach->Assemble()");           // PF_linear_par_partial.cpp:118-121
         check(lpf_jacobi_setup(ctx_), "OperatorJacobiSmoother");        // :124
         state_ = (double *)lpf_dev_alloc(sizeof(double) * 2 * (ns_ ? ns_ : 1));
@@ -149,28 +201,6 @@ private:
     lpf_ctx *ctx_ = nullptr;
     double *state_ = nullptr;
     int ns_, ndof_;
-};
-
-// ---- one std::thread per GPU ("mpirun -np N") ----
-struct World {
-    int nranks;
-    unsigned char nccl_id[128];
-    std::vector<double> reduce_buf;
-    explicit World(int n) : nranks(n), reduce_buf(n, 0.0)
-    {
-        if (n > 1) check(lpf_comm_unique_id(nccl_id), "lpf_comm_unique_id");
-        const int ndev = lpf_device_count();
-        if (ndev < n) throw std::runtime_error("need " + std::to_string(n) + " GPUs, found " + std::to_string(ndev));
-    }
-    void run(const std::function<void(int)> &fn)
-    {
-        std::vector<std::thread> th;
-        std::vector<std::string> err(nranks);
-        for (int r = 0; r < nranks; r++)
-            th.emplace_back([&, r] { try { fn(r); } catch (const std::exception &e) { err[r] = e.what(); } });
-        for (auto &t : th) t.join();
-        for (int r = 0; r < nranks; r++) if (!err[r].empty()) throw std::runtime_error("rank " + std::to_string(r) + ": " + err[r]);
-    }
 };
 
 }  // namespace lpfd

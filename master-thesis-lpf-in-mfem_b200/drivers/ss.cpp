@@ -44,7 +44,7 @@ int main(int argc, char *argv[])
         for (int order : orders) {
             std::unique_ptr<Mesh> mesh(Mesh::FromName(mesh_name));
             for (int i = 0; i < par_ref_levels; i++) mesh->UniformRefinement();
-            World world(num_procs);
+            World world(num_procs, std::string(a.get("--comm", "p2p")) == "nccl");
             std::mutex mu;
             double max_time = 0.0;
             long dofs = 0;
@@ -58,7 +58,7 @@ int main(int argc, char *argv[])
                     state[s] = w.eta(0.0, d.surf_xy[2 * s], d.surf_xy[2 * s + 1]);
                     state[ns + s] = w.phi_fs(0.0, d.surf_xy[2 * s], d.surf_xy[2 * s + 1]);
                 }
-                RhsLinear surface(fespace, myid, world.nccl_id);
+                RhsLinear surface(fespace, myid, world);
                 surface.Setup(w.params(0.0, false, rel_tol, max_iter), nullptr, nullptr);
                 surface.SetState(state);
                 double t = 0.0;

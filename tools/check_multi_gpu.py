@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--mesh", default="tank")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
     a = ap.parse_args()
     lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
     world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
@@ -43,11 +44,16 @@ def main():
     p = a.order
     sp = lpf.Space(mesh, p, nranks=world, rank=rank)
     ctx = lpf.Context(sp, device=local, stream=stream)
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if a.comm == "p2p":
+        ctx.p2p_connect(dist)                       # our own NVLink peer-memory exchange, no NCCL inside the solver
+    else:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        ctx.comm_init(idt.cpu().numpy().tobytes())
     if rank == 0:
-        idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
-    dist.broadcast(idt, 0)
-    ctx.comm_init(idt.cpu().numpy().tobytes())
+        print(f"communication: {a.comm}", flush=True)
     ctx.pa_setup()
     ctx.jacobi_setup()
 
@@ -125,6 +131,8 @@ def main():
     if rank == 0:
         print(f"    stage iterations: single {its_s}, {world} GPUs {its_m}")
         print("MULTI-GPU PARITY: " + ("OK" if not fails else "FAILED " + str(fails)), flush=True)
+    if a.comm == "p2p":
+        check("p2p flag waits timed out", float(ctx.p2p_error()), 0.5)
     ctx.close(); sctx.close()
     dist.destroy_process_group()
     sys.exit(1 if fails else 0)

@@ -15,6 +15,7 @@
 #include "pa_kernels.cuh"
 #include "pa_apply_pipe.cuh"
 #include "pa_apply_tma.cuh"
+#include "pa_apply_eo.cuh"
 #include "vec_kernels.cuh"
 #include "p2p.cuh"
 
@@ -162,13 +163,13 @@ int apply_pipe_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y,
     return LPF_OK;
 }
 
-template <int P, int E, int MINB>
+template <int P, int E, int MINB, bool EO = false>
 int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
 {
     using C = TmaCfg<P, E>;
     static int blocks_per_sm[16] = {0};
-    auto kd = pa_apply_tma_kernel<P, E, true, MINB>;
-    auto kn = pa_apply_tma_kernel<P, E, false, MINB>;
+    auto kd = EO ? pa_apply_eo_kernel<P, E, true, MINB> : pa_apply_tma_kernel<P, E, true, MINB>;
+    auto kn = EO ? pa_apply_eo_kernel<P, E, false, MINB> : pa_apply_tma_kernel<P, E, false, MINB>;
     int &bps = blocks_per_sm[c->dev & 15];
     if (bps == 0) {
         CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -192,11 +193,14 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
 // 200+ the register-pipelined one, so every design that profiles/ discusses stays measurable.
 // E-vector applies (AddMultPA adapter entry point) use the one-batch-per-CTA kernel.
 #define LPF_TMA(P, E, MINB) return apply_tma_launch_t<P, E, MINB>(c, gmap, x, y, den, status)
+#define LPF_EO(P, E, MINB) return apply_tma_launch_t<P, E, MINB, true>(c, gmap, x, y, den, status)
 #define LPF_OLD(P, E, PF) return apply_launch_t<P, E, PF, EVEC, 1>(c, gmap, x, y, den, status)
 template <bool EVEC>
 int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
 {
-    const int v = c->variant;
+    int v = c->variant;
+    const bool plain = (v == 20);
+    if (plain) v = -1;            // falls through to the default (E, MINB) of the plain-contraction TMA kernel
     if (EVEC || v >= 100) {
         switch (c->p) {
             case 1: LPF_OLD(1, 16, true);
@@ -216,6 +220,30 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
         }
     }
     if constexpr (!EVEC) {
+        if (v == 0) {                 // tuned defaults (profiles/r01_sweep_orders.txt): even-odd kernel from order 3 up
+            switch (c->p) {
+                case 3: LPF_EO(3, 8, 2);
+                case 4: LPF_EO(4, 3, 3);
+                case 5: LPF_EO(5, 3, 2);
+                case 6: LPF_EO(6, 2, 2);
+                case 7: LPF_EO(7, 1, 2);
+                case 8: LPF_EO(8, 1, 2);
+                default: break;       // orders 1, 2: plain contractions below
+            }
+        }
+        if (v >= 30 && v < 40) {      // even-odd contractions (pa_apply_eo.cuh)
+            switch (c->p) {
+                case 1: if (v == 31) LPF_EO(1, 32, 2); LPF_EO(1, 16, 3);
+                case 2: if (v == 31) LPF_EO(2, 16, 2); LPF_EO(2, 8, 3);
+                case 3: if (v == 31) LPF_EO(3, 8, 2); LPF_EO(3, 5, 3);
+                case 4: if (v == 31) LPF_EO(4, 4, 3); if (v == 32) LPF_EO(4, 2, 5); LPF_EO(4, 3, 3);
+                case 5: if (v == 31) LPF_EO(5, 3, 2); if (v == 32) LPF_EO(5, 2, 4); LPF_EO(5, 2, 3);
+                case 6: if (v == 31) LPF_EO(6, 3, 1); if (v == 32) LPF_EO(6, 2, 3); LPF_EO(6, 2, 2);
+                case 7: if (v == 31) LPF_EO(7, 1, 2); if (v == 32) LPF_EO(7, 2, 2); LPF_EO(7, 2, 1);
+                case 8: if (v == 31) LPF_EO(8, 1, 2); LPF_EO(8, 2, 1);
+                default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
+            }
+        }
         switch (c->p) {
             case 1: if (v == 1) LPF_TMA(1, 8, 4); if (v == 2) LPF_TMA(1, 32, 2); LPF_TMA(1, 16, 3);
             case 2: if (v == 1) LPF_TMA(2, 4, 5); if (v == 2) LPF_TMA(2, 16, 2); LPF_TMA(2, 8, 3);
@@ -243,6 +271,7 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
     return LPF_ERR_UNSUPPORTED;
 }
 #undef LPF_TMA
+#undef LPF_EO
 #undef LPF_OLD
 
 
@@ -401,6 +430,33 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         std::copy(bs.qpts.begin(), bs.qpts.end(), t.qpts);
         std::copy(bs.qwts.begin(), bs.qwts.end(), t.qwts);
         CUDA_TRY(cudaMemcpyToSymbol(c_tab, &t, sizeof(t), sizeof(LpfBasisTab) * c->p));
+        // even / odd half tables of the (anti)symmetric B and G (pa_apply_eo.cuh)
+        LpfEoTab eo;
+        std::memset(&eo, 0, sizeof(eo));
+        const int D = bs.D, Q = bs.Q, DC = (D + 1) / 2, DH = D / 2, QC = (Q + 1) / 2, QH = Q / 2;
+        auto Bm = [&](int q, int d) { return bs.B[(size_t)q * D + d]; };
+        auto Gm = [&](int q, int d) { return bs.G[(size_t)q * D + d]; };
+        for (int q = 0; q < QC; q++) {
+            for (int d = 0; d < DC; d++) {
+                eo.BeF[q * DC + d] = d < DH ? 0.5 * (Bm(q, d) + Bm(q, D - 1 - d)) : Bm(q, d);
+                eo.GeF[q * DC + d] = d < DH ? 0.5 * (Gm(q, d) + Gm(q, D - 1 - d)) : Gm(q, d);
+            }
+            for (int d = 0; d < DH; d++) {
+                eo.BoF[q * DH + d] = 0.5 * (Bm(q, d) - Bm(q, D - 1 - d));
+                eo.GoF[q * DH + d] = 0.5 * (Gm(q, d) - Gm(q, D - 1 - d));
+            }
+        }
+        for (int d = 0; d < DC; d++) {
+            for (int q = 0; q < QC; q++) {
+                eo.BeT[d * QC + q] = q < QH ? 0.5 * (Bm(q, d) + Bm(Q - 1 - q, d)) : Bm(q, d);
+                eo.GeT[d * QC + q] = q < QH ? 0.5 * (Gm(q, d) + Gm(Q - 1 - q, d)) : Gm(q, d);
+            }
+            for (int q = 0; q < QH; q++) {
+                eo.BoT[d * QH + q] = 0.5 * (Bm(q, d) - Bm(Q - 1 - q, d));
+                eo.GoT[d * QH + q] = 0.5 * (Gm(q, d) - Gm(Q - 1 - q, d));
+            }
+        }
+        CUDA_TRY(cudaMemcpyToSymbol(c_eo, &eo, sizeof(eo), sizeof(LpfEoTab) * c->p));
     }
     if (d->corners) LPF_TRY(upload(c->corners, d->corners, (size_t)c->ne * 24, &c->bytes));
     if (d->jac) LPF_TRY(upload(c->jac, d->jac, (size_t)c->ne * Q3 * 9, &c->bytes));

@@ -1,0 +1,288 @@
+// Even-odd variant of the persistent TMA-staged PA apply kernel (same pipeline, staging and shared-memory
+// layout as pa_apply_tma_kernel; only the 1-D contractions differ).
+//
+// Gauss-Lobatto nodes and Gauss-Legendre points are symmetric about 1/2, so B[Q-1-q][D-1-d] = B[q][d] and
+// G[Q-1-q][D-1-d] = -G[q][d].  Splitting a line into its even and odd parts e = u + rev(u), o = u - rev(u)
+// turns one Q x D contraction into a ceil(Q/2) x ceil(D/2) and a ceil(Q/2) x floor(D/2) one plus D + Q
+// additions: 26 instead of 30 FP64 operations per line at p = 4, 64 instead of 90 at p = 8, and half as many
+// coefficient loads (LDCU) -- the two instruction classes that made the kernel issue-bound (ncu: 46 % DFMA,
+// 25 % LDCU, profiles/r01_apply_ncu.md).  The half-size tables are built on the host from B and G
+// (lpf_device.cu, fill_eo_tables) directly from their definitions:
+//   forward   out[q] = sum_d M[q][d] in[d]:  MeF[q][d] = (M[q][d] + M[q][D-1-d]) / 2, MoF[q][d] = (M[q][d] - M[q][D-1-d]) / 2
+//   transpose out[d] = sum_q M[q][d] in[q]:  MeT[d][q] = (M[q][d] + M[Q-1-q][d]) / 2, MoT[d][q] = (M[q][d] - M[Q-1-q][d]) / 2
+// (middle columns un-halved), and  out[j] = se + so,  out[N-1-j] = sigma (se - so)  with sigma = +1 for B, -1 for G.
+#pragma once
+#include "pa_apply_tma.cuh"
+
+struct LpfEoTab {
+    static constexpr int MH = (LPF_MAXP + 3) / 2;     // ceil(Q_max / 2)
+    double BeF[MH * MH], BoF[MH * MH], GeF[MH * MH], GoF[MH * MH];   // [QC][DC], [QC][DH]
+    double BeT[MH * MH], BoT[MH * MH], GeT[MH * MH], GoT[MH * MH];   // [DC][QC], [DC][QH]
+};
+
+__constant__ LpfEoTab c_eo[LPF_MAXP + 1];
+
+// out (+)= M in for a (anti)symmetric NO x NI matrix given by its even / odd half tables.
+template <int NI, int NO, int SIGN, bool ACC>
+__device__ __forceinline__ void eo_contract(const double *__restrict__ Me, const double *__restrict__ Mo,
+                                            const double (&e)[(NI + 1) / 2], const double (&o)[NI / 2 > 0 ? NI / 2 : 1],
+                                            double (&out)[NO])
+{
+    constexpr int NIC = (NI + 1) / 2, NIH = NI / 2, NOC = (NO + 1) / 2, NOH = NO / 2;
+#pragma unroll
+    for (int j = 0; j < NOC; j++) {
+        const bool mid = (j >= NOH);                  // middle output row (NO odd): only one parity survives
+        double se = 0.0, so = 0.0;
+        if (!(mid && SIGN < 0)) {
+#pragma unroll
+            for (int i = 0; i < NIC; i++) se = fma(Me[j * NIC + i], e[i], se);
+        }
+        if (!(mid && SIGN > 0)) {
+#pragma unroll
+            for (int i = 0; i < NIH; i++) so = fma(Mo[j * NIH + i], o[i], so);
+        }
+        if (ACC) out[j] += se + so; else out[j] = se + so;
+        if (!mid) {
+            const double r = SIGN > 0 ? se - so : so - se;
+            if (ACC) out[NO - 1 - j] += r; else out[NO - 1 - j] = r;
+        }
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N + 1) / 2], double (&o)[N / 2 > 0 ? N / 2 : 1])
+{
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) { e[i] = in[i] + in[N - 1 - i]; o[i] = in[i] - in[N - 1 - i]; }
+    if (N & 1) e[N / 2] = in[N / 2];
+}
+
+template <int P, int E, bool DEN, int MINB>
+__global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
+pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
+                   double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status)
+{
+    using C = TmaCfg<P, E>;
+    constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
+    constexpr int DP3 = C::DP3, QE = C::QE;
+    constexpr int DC = (D + 1) / 2, DH = D / 2 > 0 ? D / 2 : 1, QC = (Q + 1) / 2, QH = Q / 2 > 0 ? Q / 2 : 1;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    if (status != nullptr && *status != 0) return;
+    double *sq = reinterpret_cast<double *>(smem_raw + C::OFF_Q);
+    int *sidx = reinterpret_cast<int *>(smem_raw + C::OFF_IDX);
+    double *smem = reinterpret_cast<double *>(smem_raw + C::OFF_WORK);
+    uint64_t *bar_q = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
+    uint64_t *bar_i = bar_q + 1;
+
+    const int tid = threadIdx.x;
+    const int nb = (ne + E - 1) / E;
+    const int ez = tid / LZ, q2 = tid - ez * LZ;
+    const int ex = tid / LX, lx = tid - ex * LX;
+    const int xdz = lx / D, xdy = lx - xdz * D;
+    const bool xrole = tid < E * LX;
+    const int ey = tid / LY, ly = tid - ey * LY;
+    const int ydz = ly / Q, yqx = ly - ydz * Q;
+    const bool yrole = tid < E * LY;
+
+    if (tid == 0) {
+        mbar_init(bar_q, 1); mbar_init(bar_i, 1); mbar_init(bar_i + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int b = blockIdx.x;
+    if (b >= nb) return;
+    auto batch_elems = [&](int bb) { return min(E, ne - bb * E); };
+    if (tid == 0) {
+        const int n0 = batch_elems(b);
+        mbar_expect_tx(bar_i, (uint32_t)(n0 * DP3 * 4));
+        bulk_g2s(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i);
+        mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
+        bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+    }
+    double xs[D], xsn[D];
+    double part = 0.0;
+    mbar_wait(bar_i, 0);
+    if (xrole && b * E + ex < ne) {
+        const int *gi = sidx + ex * DP3 + lx * D;
+#pragma unroll
+        for (int i = 0; i < D; i++) { const int g = gi[i]; xs[i] = g >= 0 ? x[g] : 0.0; }
+    }
+
+    uint32_t it = 0;
+    for (; b < nb; b += gridDim.x, it++) {
+        const int e0 = b * E;
+        const int bn = b + gridDim.x;
+        const int e0n = bn * E;
+        const bool has_next = bn < nb;
+        const bool xvalid = xrole && (e0 + ex) < ne;
+        const bool yvalid = yrole && (e0 + ey) < ne;
+        const bool zvalid = (e0 + ez) < ne;
+        const bool xnext = xrole && has_next && (e0n + ex) < ne;
+        const int cur = it & 1, nxt = cur ^ 1;
+        // loop-variant (always zero) table offset: keeps the compiler from hoisting the coefficients out of the
+        // batch loop into (too few) uniform registers, see pa_apply_tma.cuh
+        const LpfEoTab &T = c_eo[P + (it >> 30)];
+
+        if (tid == 0 && has_next) {
+            const int n1 = batch_elems(bn);
+            fence_proxy_async();
+            mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
+            bulk_g2s(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt);
+        }
+
+        // ---- X stage: (B_x u, G_x u) on the line (dz,dy) ----
+        if (xvalid) {
+            double e[DC], o[DH], sb[Q], sg[Q];
+            eo_split<D>(xs, e, o);
+            eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, sb);
+            eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, sg);
+            double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
+#pragma unroll
+            for (int q = 0; q < Q; q++) { a[q] = sb[q]; a[C::SAA + q] = sg[q]; }
+        }
+        __syncthreads();
+
+        // ---- Y stage: line (dz,qx) ----
+        if (yvalid) {
+            const double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
+            double ua[D], ub[D];
+#pragma unroll
+            for (int i = 0; i < D; i++) { ua[i] = a[i * C::SAY]; ub[i] = a[C::SAA + i * C::SAY]; }
+            double e[DC], o[DH], s0[Q], s1[Q], s2[Q];
+            eo_split<D>(ua, e, o);
+            eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, s0);      // B_y B_x u
+            eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, s1);      // G_y B_x u
+            eo_split<D>(ub, e, o);
+            eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, s2);      // B_y G_x u
+            double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
+#pragma unroll
+            for (int q = 0; q < Q; q++) { bb[q * Q] = s0[q]; bb[C::SBA + q * Q] = s1[q]; bb[2 * C::SBA + q * Q] = s2[q]; }
+        }
+        __syncthreads();
+
+        // ---- Z stage: column (qy,qx): forward z for all levels, D tensor per level, backward z ----
+        mbar_wait(bar_q, it & 1);
+        if (zvalid) {
+            double *bb = smem + ez * C::ES + C::OFFB + q2;
+            const double2 *sqv = reinterpret_cast<const double2 *>(sq) + (size_t)ez * (QE / 2) + q2;
+            double g0[Q], g1[Q], g2[Q];
+            {
+                double u[D], e[DC], o[DH];
+#pragma unroll
+                for (int i = 0; i < D; i++) u[i] = bb[2 * C::SBA + i * C::SBZ];       // G_x B_y u  -> B_z
+                eo_split<D>(u, e, o);
+                eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, g0);
+#pragma unroll
+                for (int i = 0; i < D; i++) u[i] = bb[C::SBA + i * C::SBZ];           // B_x G_y u  -> B_z
+                eo_split<D>(u, e, o);
+                eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, g1);
+#pragma unroll
+                for (int i = 0; i < D; i++) u[i] = bb[i * C::SBZ];                    // B_x B_y u  -> G_z
+                eo_split<D>(u, e, o);
+                eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, g2);
+            }
+#pragma unroll
+            for (int qz = 0; qz < Q; qz++) {
+                const double2 d0 = sqv[(qz * 3 + 0) * LZ], d1 = sqv[(qz * 3 + 1) * LZ], d2 = sqv[(qz * 3 + 2) * LZ];
+                const double a0 = g0[qz], a1 = g1[qz], a2 = g2[qz];
+                g0[qz] = d0.x * a0 + d0.y * a1 + d1.x * a2;
+                g1[qz] = d0.y * a0 + d1.y * a1 + d2.x * a2;
+                g2[qz] = d1.x * a0 + d2.x * a1 + d2.y * a2;
+            }
+            {
+                double c[D], e[QC], o[QH];
+                eo_split<Q>(g0, e, o);
+                eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, c);
+#pragma unroll
+                for (int i = 0; i < D; i++) bb[2 * C::SBA + i * C::SBZ] = c[i];
+                eo_split<Q>(g1, e, o);
+                eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, c);
+#pragma unroll
+                for (int i = 0; i < D; i++) bb[C::SBA + i * C::SBZ] = c[i];
+                eo_split<Q>(g2, e, o);
+                eo_contract<Q, D, -1, false>(T.GeT, T.GoT, e, o, c);
+#pragma unroll
+                for (int i = 0; i < D; i++) bb[i * C::SBZ] = c[i];
+            }
+        }
+        __syncthreads();
+
+        if (tid == 0 && has_next) {
+            const int n1 = batch_elems(bn);
+            fence_proxy_async();
+            mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
+            bulk_g2s(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q);
+        }
+        if (has_next) mbar_wait(bar_i + nxt, ((it + 1) >> 1) & 1);
+        if (xnext) {
+            const int *gi = sidx + nxt * E * DP3 + ex * DP3 + lx * D;
+#pragma unroll
+            for (int i = 0; i < D; i++) { const int g = gi[i]; xsn[i] = g >= 0 ? x[g] : 0.0; }
+        }
+
+        // ---- Yt stage: line (dz,qx) ----
+        if (yvalid) {
+            const double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
+            double v[Q], e[QC], o[QH], ta[D], tb[D];
+#pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = bb[q * Q];
+            eo_split<Q>(v, e, o);
+            eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, ta);
+#pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = bb[C::SBA + q * Q];
+            eo_split<Q>(v, e, o);
+            eo_contract<Q, D, -1, true>(T.GeT, T.GoT, e, o, ta);
+#pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = bb[2 * C::SBA + q * Q];
+            eo_split<Q>(v, e, o);
+            eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, tb);
+            double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
+#pragma unroll
+            for (int i = 0; i < D; i++) { a[i * C::SAY] = ta[i]; a[C::SAA + i * C::SAY] = tb[i]; }
+        }
+        __syncthreads();
+
+        // ---- Xt stage + scatter-add ----
+        if (xvalid) {
+            const double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
+            const int *gi = sidx + cur * E * DP3 + ex * DP3 + lx * D;
+            double v[Q], e[QC], o[QH], yv[D];
+#pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = a[q];
+            eo_split<Q>(v, e, o);
+            eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, yv);
+#pragma unroll
+            for (int q = 0; q < Q; q++) v[q] = a[C::SAA + q];
+            eo_split<Q>(v, e, o);
+            eo_contract<Q, D, -1, true>(T.GeT, T.GoT, e, o, yv);
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                const int g = gi[i];
+                if (g >= 0) {
+                    atomicAdd(y + g, yv[i]);
+                    if (DEN) part = fma(xs[i], yv[i], part);
+                }
+            }
+        }
+        if (xnext) {
+#pragma unroll
+            for (int i = 0; i < D; i++) xs[i] = xsn[i];
+        }
+        __syncthreads();
+    }
+
+    if (DEN && den_slots != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        __shared__ double wsum[32];
+        const int w = tid >> 5, nw = (C::NT + 31) >> 5;
+        if ((tid & 31) == 0) wsum[w] = part;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int i = 0; i < nw; i++) s += wsum[i];
+            atomicAdd(den_slots + (blockIdx.x & 255), s);
+        }
+    }
+}

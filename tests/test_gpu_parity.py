@@ -73,7 +73,8 @@ def test_qdata_apply_diag_all_orders(lpf, orc, cuda, tank, p):
     ctx.close()
 
 
-@pytest.mark.parametrize("p,variant", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (5, 1), (5, 2), (6, 1), (6, 2), (7, 1), (8, 1)])
+@pytest.mark.parametrize("p,variant", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (5, 1), (5, 2), (6, 1), (6, 2), (7, 1), (8, 1)]
+                         + [(p, v) for p in range(1, 9) for v in (30, 31)] + [(4, 32), (5, 32), (6, 32), (7, 32)])
 def test_apply_kernel_alternative_variants(lpf, orc, cuda, p, variant):
     """The non-default (elements per CTA, CTAs per SM) instantiations of the persistent kernel, forced through
     several batches per CTA."""
@@ -92,7 +93,7 @@ def test_apply_kernel_alternative_variants(lpf, orc, cuda, p, variant):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 12, 14, 15, 100, 101, 102, 103, 104])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 12, 14, 15, 20, 30, 31, 32, 100, 101, 102, 103, 104])
 def test_apply_kernel_variants_p4(lpf, orc, cuda, variant):
     """Every compiled (elements-per-CTA, pipelining) variant of the order-4 kernel, on a mesh whose element
     count (7x1x3 refined once = 168, perturbed) is ragged for every batch size and spans several batches

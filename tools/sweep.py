@@ -16,7 +16,7 @@ def main():
     import torch
     ap = argparse.ArgumentParser()
     ap.add_argument("--orders", default="1,2,3,4,5,6,7,8")
-    ap.add_argument("--variants", default="0,1,2")
+    ap.add_argument("--variants", default="0,20")
     ap.add_argument("--refine-low", type=int, default=2, help="refinements for orders <= 4")
     ap.add_argument("--refine-high", type=int, default=1, help="refinements for orders >= 5")
     ap.add_argument("--reps", type=int, default=20)

@@ -107,6 +107,9 @@ struct lpf_ctx {
     int *p2p_send_nbr[2] = {nullptr, nullptr};
     double **p2p_dst[2] = {nullptr, nullptr};
     P2PDev p2p{};
+    P2PTail tail{};           // set around PCG applies when the exchange rides on the apply kernel
+    unsigned int *p2p_done = nullptr;
+    int p2p_fuse = 1;         // option: fuse halo-sum / all-reduces into the apply / update kernels
     // host staging for *_host entry points
     double *hx = nullptr, *hy = nullptr;
     // CUDA graph of one PCG chunk
@@ -180,8 +183,8 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
     const int nb = (c->ne + E - 1) / E;
     if (nb == 0) return LPF_OK;
     const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
-    if (den) kd<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
-    else kn<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
+    if (den) kd<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status, c->tail);
+    else kn<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status, c->tail);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
@@ -336,6 +339,8 @@ int p2p_create(lpf_ctx *c)
     CUDA_TRY(cudaMemcpy(c->box, &h, sizeof(h), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void **)&c->p2p_local, sizeof(P2PLocal)));
     CUDA_TRY(cudaMemset(c->p2p_local, 0, sizeof(P2PLocal)));
+    CUDA_TRY(cudaMalloc((void **)&c->p2p_done, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(c->p2p_done, 0, sizeof(unsigned int)));
     c->bytes += c->box_bytes;
     return LPF_OK;
 }
@@ -587,7 +592,7 @@ void lpf_destroy(lpf_ctx *c)
     for (void *p : ptrs) if (p) cudaFree(p);
     free_halo(c->halo); free_halo(c->shalo);
     for (size_t r = 0; r < c->peers.size(); r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
-    void *pp[] = {c->box, c->p2p_local, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1], c->p2p_dst[0], c->p2p_dst[1]};
+    void *pp[] = {c->box, c->p2p_local, c->p2p_done, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1], c->p2p_dst[0], c->p2p_dst[1]};
     for (void *p : pp) if (p) cudaFree(p);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->state_pinned) cudaFreeHost(c->state_pinned);
@@ -619,6 +624,7 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "use_graph") c->use_graph = (int)value;
     else if (k == "pcg_chunk") { if (value < 1) { lpf::set_error("pcg_chunk must be >= 1"); return LPF_ERR_ARG; } c->chunk = (int)value; }
     else if (k == "skip_zero_apply") c->skip_zero_apply = (int)value;
+    else if (k == "p2p_fuse") c->p2p_fuse = (int)value;
     else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
     if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
@@ -812,10 +818,36 @@ int multi_reduce(lpf_ctx *c, int mode)
 }
 
 // one CG iteration body: update (+ dot), direction, apply (+ den); all skip themselves once status != 0
+bool p2p_fused(const lpf_ctx *c)
+{
+    const bool tail_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
+    // the tail runs in ONE CTA: worth it only while the interface is small (measured: 2 x 585 dofs at big8 p=4 breaks even
+    // with NCCL, 2 x 8481 dofs is 2x slower than separate multi-CTA pack / unpack kernels)
+    return c->p2p_on && c->p2p_fuse && !c->ess_general && tail_kernel && c->halo.n_nbr > 0 && c->halo.n_nbr <= 32 && c->halo.total <= 2048;
+}
+
+// constrained apply whose last CTA also does the halo-sum and the all-reduce of (d, A d)
+int apply_with_tail(lpf_ctx *c, const double *x, double *y)
+{
+    c->tail.enabled = 1; c->tail.with_den = 1; c->tail.d = c->p2p; c->tail.h = c->p2p_plan[0];
+    c->tail.st = c->st; c->tail.den_slots = c->den_slots; c->tail.done = c->p2p_done;
+    const int rc = apply_launch<false>(c, c->gmap_c, x, y, c->den_slots, &c->st->status);
+    c->tail.enabled = 0;
+    return rc;
+}
+
 int pcg_iteration(lpf_ctx *c)
 {
     const int n = c->ndof, g = vec_grid(n, c->sm_count);
     const bool multi = c->nranks > 1;
+    if (p2p_fused(c)) {
+        // three launches, as on one GPU: the betanom all-reduce runs in the last block of the update kernel, the
+        // halo-sum and the (d, A d) all-reduce in the last CTA of the apply kernel (peer-memory stores + flags)
+        pcg_update_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->partials, c->p2p);
+        pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
+        c->launches += 2;
+        return apply_with_tail(c, c->d, c->ad);
+    }
     if (multi) {
         pcg_update_kernel<true><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->den_slots, c->partials);
         c->launches++;
@@ -842,7 +874,7 @@ int pcg_chunk(lpf_ctx *c)
         for (int i = 0; i < c->chunk; i++) LPF_TRY(pcg_iteration(c));
         return LPF_OK;
     }
-    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk || c->pcg_graph_general != c->ess_general) {
+    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk || c->pcg_graph_general != c->ess_general + 2 * (int)p2p_fused(c)) {
         if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
         cudaGraph_t graph = nullptr;
         const long l0 = c->launches;
@@ -857,7 +889,7 @@ int pcg_chunk(lpf_ctx *c)
         CUDA_TRY(cudaGraphInstantiate(&c->pcg_graph, graph, 0));
         cudaGraphDestroy(graph);
         c->pcg_graph_chunk = c->chunk;
-        c->pcg_graph_general = c->ess_general;
+        c->pcg_graph_general = c->ess_general + 2 * (int)p2p_fused(c);
     }
     CUDA_TRY(cudaGraphLaunch(c->pcg_graph, c->stream));
     c->launches += c->pcg_graph_launches;
@@ -886,7 +918,11 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         c->launches++;
         t = c->tmp;
     }
-    if (multi) {
+    if (p2p_fused(c)) {
+        pcg_init_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials, c->p2p);
+        c->launches++;
+        LPF_TRY(apply_with_tail(c, c->d, c->ad));
+    } else if (multi) {
         pcg_init_kernel<true><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
         LPF_TRY(multi_reduce(c, P2P_RED_NOM));
@@ -894,11 +930,13 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         pcg_init_kernel<false><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, nullptr, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
     }
-    LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
-    LPF_TRY(ess_fix(c));
-    if (multi) {
-        LPF_TRY(halo_sum(c, c->halo, c->ad));
-        LPF_TRY(multi_reduce(c, P2P_RED_DEN));
+    if (!p2p_fused(c)) {
+        LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+        LPF_TRY(ess_fix(c));
+        if (multi) {
+            LPF_TRY(halo_sum(c, c->halo, c->ad));
+            LPF_TRY(multi_reduce(c, P2P_RED_DEN));
+        }
     }
     CUDA_TRY(cudaGetLastError());
     // iterate in chunks; the only host round trip is the status poll after each chunk

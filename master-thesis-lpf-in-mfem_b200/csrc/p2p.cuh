@@ -74,6 +74,30 @@ __device__ __forceinline__ bool p2p_wait(const unsigned long long *flag, unsigne
     return true;
 }
 
+// Sum of one double over all ranks, executed by one full warp; lane r sends this rank's value to rank r and
+// waits for rank r's value.  Returns the sum (identical bits on every rank: fixed rank order) in every lane.
+__device__ __forceinline__ double p2p_allreduce_warp(const P2PDev &d, double local_val)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned long long seq = d.local->red_seq + 1;
+    const int par = (int)(seq & 1);
+    __syncwarp();
+    if (lane < d.nranks) {
+        P2PBox *peer = d.peers[lane];
+        peer->red_val[par][d.rank] = local_val;
+        __threadfence_system();
+        p2p_store_flag(&peer->red_flag[par][d.rank], seq);
+        p2p_wait(&d.mine->red_flag[par][lane], seq, &d.local->error);
+    }
+    __syncwarp();
+    double s = 0.0;
+    for (int r = 0; r < d.nranks; r++) s += ((volatile double *)d.mine->red_val[par])[r];
+    __syncwarp();
+    if (lane == 0) d.local->red_seq = seq;
+    __syncwarp();
+    return s;
+}
+
 // ---- scalar all-reduce (sum) + what the PCG does with the result -----------------------------------------
 enum { P2P_RED_PLAIN = 0, P2P_RED_NOM = 1, P2P_RED_BETA = 2, P2P_RED_DEN = 3 };
 
@@ -90,20 +114,8 @@ __global__ void p2p_allreduce_kernel(P2PDev d, double *val, int mode, PcgState *
         if (lane == 0) local_val = s;
     } else if (lane == 0) local_val = *val;
     __syncwarp();
-    const unsigned long long seq = d.local->red_seq + 1;
-    const int par = (int)(seq & 1);
-    if (lane < d.nranks) {
-        P2PBox *peer = d.peers[lane];
-        peer->red_val[par][d.rank] = local_val;
-        __threadfence_system();
-        p2p_store_flag(&peer->red_flag[par][d.rank], seq);
-        p2p_wait(&d.mine->red_flag[par][lane], seq, &d.local->error);
-    }
-    __syncwarp();
+    const double s = p2p_allreduce_warp(d, local_val);
     if (lane == 0) {
-        double s = 0.0;
-        for (int r = 0; r < d.nranks; r++) s += ((volatile double *)d.mine->red_val[par])[r];   // rank order: identical on all ranks
-        d.local->red_seq = seq;
         if (mode == P2P_RED_NOM) pcg_finalize_nom(st, s);
         else if (mode == P2P_RED_BETA) { if (st->status == PCG_RUNNING) pcg_finalize_beta(st, s); }
         else if (mode == P2P_RED_DEN) st->red[1] = s;
@@ -156,4 +168,122 @@ __global__ void p2p_unpack_kernel(P2PDev d, P2PPlanDev h, int plan, double *__re
     }
     __syncthreads();
     if (is_last && threadIdx.x == 0) d.local->halo_seq[plan] = seq;
+}
+
+// ---- halo-sum + (d, A d) all-reduce fused into the tail of the apply kernel ---------------------------------
+// Every CTA of the persistent apply kernel calls p2p_apply_tail() after its last batch.  The CTA that arrives
+// last (all scatter-adds of this rank are then globally visible) packs the interface values straight into the
+// neighbours' mailboxes, raises their flags, waits for theirs, adds the partial sums in rank order and finally
+// all-reduces the PCG denominator -- the collective rides on the compute kernel, no extra launch, no NCCL.
+struct P2PTail {
+    int enabled, with_den;
+    P2PDev d;
+    P2PPlanDev h;
+    PcgState *st;
+    double *den_slots;
+    unsigned int *done;
+};
+
+__device__ __forceinline__ void p2p_apply_tail(const P2PTail &t, double *__restrict__ y)
+{
+    __shared__ bool tail_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int n = atomicInc(t.done, gridDim.x - 1);
+        tail_last = (n == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!tail_last) return;
+    __threadfence();
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const P2PPlanDev &h = t.h;
+    if (h.n_nbr > 0) {
+        const unsigned long long seq = t.d.local->halo_seq[0] + 1;
+        const int par = (int)(seq & 1);
+        for (int i = tid; i < h.total; i += nt) {
+            const int k = h.send_nbr[i];
+            h.dst[par * h.n_nbr + k][i - h.nbr_offset[k]] = __ldcg(y + h.send_dofs[i]);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < h.n_nbr) {
+            p2p_store_flag(&t.d.peers[h.nbr_rank[tid]]->halo_flag[0][par][t.d.rank], seq);
+            p2p_wait(&t.d.mine->halo_flag[0][par][h.nbr_rank[tid]], seq, &t.d.local->error);
+        }
+        __syncthreads();
+        const volatile double *recv = h.recv[par];
+        for (int i = tid; i < h.n_shared; i += nt) {
+            const int dof = h.shared[i];
+            const double own = __ldcg(y + dof);
+            double s = 0.0;
+            for (int j = h.red_off[i]; j < h.red_off[i + 1]; j++) s += (h.red_src[j] < 0) ? own : recv[h.red_src[j]];
+            y[dof] = s;
+        }
+        __syncthreads();
+        if (tid == 0) t.d.local->halo_seq[0] = seq;
+    }
+    if (t.with_den && tid < 32) {
+        double s = 0.0;
+        for (int i = tid; i < LPF_DEN_SLOTS; i += 32) { s += __ldcg(t.den_slots + i); t.den_slots[i] = 0.0; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double tot = p2p_allreduce_warp(t.d, s);
+        if (tid == 0) t.st->red[1] = tot;
+    }
+}
+
+// ---- PCG vector kernels with the cross-rank reduction inside (last block = one flag round trip, no extra launch) ----
+__global__ void pcg_init_p2p_kernel(int n, const double *__restrict__ b, const double *__restrict__ t,
+                                    const double *__restrict__ dinv, const uint8_t *__restrict__ owned,
+                                    double *__restrict__ r, double *__restrict__ z, double *__restrict__ d,
+                                    double *__restrict__ ad, PcgState *st, double *partials, P2PDev pd)
+{
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double ri = t ? b[i] - t[i] : b[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri; z[i] = zi; d[i] = zi; ad[i] = 0.0;
+        if (owned[i]) acc = fma(zi, ri, acc);
+    }
+    __shared__ double loc;
+    const bool last = grid_sum_finalize(acc, partials, &st->counter, [&](double s) { loc = s; });
+    if (last) {
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const double tot = p2p_allreduce_warp(pd, loc);
+            if (threadIdx.x == 0) pcg_finalize_nom(st, tot);
+        }
+    }
+}
+
+__global__ void pcg_update_p2p_kernel(int n, double *__restrict__ x, double *__restrict__ r, double *__restrict__ z,
+                                      const double *__restrict__ d, const double *__restrict__ ad,
+                                      const double *__restrict__ dinv, const uint8_t *__restrict__ owned, PcgState *st,
+                                      double *partials, P2PDev pd)
+{
+    if (st->status != PCG_RUNNING) return;
+    const double den = st->red[1];                  // all-reduced by the tail of the previous apply
+    if (den == 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { st->den = den; st->status = PCG_BREAKDOWN; st->final_iter = st->iter > 1 ? st->iter : 0; }
+        return;
+    }
+    const double alpha = st->nom / den;
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, d[i], x[i]);
+        const double ri = fma(-alpha, ad[i], r[i]);
+        const double zi = dinv[i] * ri;
+        r[i] = ri; z[i] = zi;
+        if (owned[i]) acc = fma(ri, zi, acc);
+    }
+    __shared__ double loc;
+    const bool last = grid_sum_finalize(acc, partials, &st->counter, [&](double s) { loc = s; });
+    if (last) {
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const double tot = p2p_allreduce_warp(pd, loc);
+            if (threadIdx.x == 0) { st->den = den; pcg_finalize_beta(st, tot); }
+        }
+    }
 }

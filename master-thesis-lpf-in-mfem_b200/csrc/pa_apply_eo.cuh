@@ -60,7 +60,8 @@ __device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N +
 template <int P, int E, bool DEN, int MINB>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
 pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
-                   double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status)
+                   double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status,
+                    const P2PTail tail)
 {
     using C = TmaCfg<P, E>;
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
@@ -285,4 +286,6 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
             atomicAdd(den_slots + (blockIdx.x & 255), s);
         }
     }
+    // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, fused into this kernel's tail
+    if (tail.enabled) p2p_apply_tail(tail, y);
 }

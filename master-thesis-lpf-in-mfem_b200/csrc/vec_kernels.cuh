@@ -43,7 +43,7 @@ __device__ __forceinline__ double block_sum(double v)
 
 // Block partial -> global array; the last block to arrive sums the array in a fixed order and calls fin(sum).
 template <class F>
-__device__ __forceinline__ void grid_sum_finalize(double v, double *partials, unsigned int *counter, F fin)
+__device__ __forceinline__ bool grid_sum_finalize(double v, double *partials, unsigned int *counter, F fin)
 {
     const double bs = block_sum(v);
     __shared__ bool is_last;
@@ -61,6 +61,7 @@ __device__ __forceinline__ void grid_sum_finalize(double v, double *partials, un
         s = block_sum(s);
         if (threadIdx.x == 0) fin(s);
     }
+    return is_last;       // true in every thread of the block that arrived last (all other blocks are done)
 }
 
 __device__ __forceinline__ void pcg_finalize_nom(PcgState *st, double nom)

@@ -94,12 +94,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(p):
-    """dram bytes per launch of the apply kernel from the committed ncu capture, if one exists."""
+def ncu_traffic(p, ne):
+    """dram bytes per launch of the apply kernel from the committed ncu capture (profiles/apply_traffic.json),
+    scaled to this launch's element count (traffic is proportional to the number of hexes)."""
     f = os.path.join(ROOT, "profiles", "apply_traffic.json")
     if os.path.exists(f):
         d = json.load(open(f))
-        return d.get(f"order{p}")
+        if f"order{p}" in d:
+            return int(d[f"order{p}"] * ne / d["hexes"][f"order{p}"])
     return None
 
 
@@ -253,8 +255,8 @@ def run_ours(a):
                    "parallelism": (f"x-slab domain decomposition x{world}, halo-sum over " + ("NVLink peer memory (own kernels)" if a.comm == "p2p" else "NCCL send/recv")) if world > 1 else "single GPU",
                    "apply_variant": a.variant},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": ncu_traffic(p), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                     "kernel_ms": ms_kernel, "kernel": "pa_apply_tma_kernel"},
+                     "traffic": ncu_traffic(p, sp.ne), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
+                     "kernel_ms": ms_kernel, "kernel": "pa_apply_eo_kernel" if p >= 3 else "pa_apply_tma_kernel"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "steps": e2e_steps, "api": "lpf_apply_T_host (pinned host x -> device -> apply -> host y)"},
         "gpu_launches": int(launches),

@@ -1,0 +1,17 @@
+"""The analytic reference curve of BASELINE config 4 (Solvers/cylinder-exact.cpp restated with scipy)."""
+import numpy as np
+
+
+def test_series_matches_wronskian_closed_form_on_the_cylinder():
+    import maccamy_fuchs as mf
+    k, a = 2.0 * np.pi, 0.5                       # lambda = 1, a = 0.5 (cylinder-diffraction.cpp:229-238)
+    phi = np.linspace(0.0, np.pi, 181)
+    e1 = mf.envelope(k, a, np.full_like(phi, a), phi)
+    e2 = mf.envelope_on_cylinder_wronskian(k, a, phi)
+    assert np.abs(e1 - e2).max() < 1e-9
+    assert 1.5 < e1.max() < 2.1 and e1.min() > 0.2           # ka = pi: strong run-up on the weather side
+    # symmetric about the wave direction, and the incident wave is recovered far from a thin cylinder
+    assert np.allclose(mf.envelope(k, a, np.full(5, a), np.array([0.3, 1.0, 2.0, 2.5, 3.0])),
+                       mf.envelope(k, a, np.full(5, a), -np.array([0.3, 1.0, 2.0, 2.5, 3.0])), atol=1e-12)
+    far = mf.envelope(k, 1e-3, np.array([5.0, 7.0]), np.array([0.4, 2.0]))
+    assert np.abs(far - 1.0).max() < 1e-4

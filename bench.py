@@ -235,8 +235,8 @@ def run_ours(a):
 
     # PCG time per RK4 step (strongscaling.cpp-like protocol: rel 1e-12, RK4, dt = T/150) on the r=1 tank
     rk = None
-    if not a.no_rk4 and world == 1:
-        rk = rk4_measure(lpf, torch, a, local, stream)
+    if not a.no_rk4:
+        rk = rk4_measure(lpf, torch, a, local, stream, world, rank, dist if world > 1 else None)
 
     if rank != 0:
         if world > 1:
@@ -272,11 +272,21 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
-def rk4_measure(lpf, torch, a, local, stream):
+def rk4_measure(lpf, torch, a, local, stream, world=1, rank=0, dist=None):
+    """PCG time per RK4 step: strongscaling.cpp protocol (rel 1e-12, dt = T/150, 1 warm-up step) on the r=1 tank; N>1 is
+    weak-scaled like the matvec (tank N times longer, one x-slab per GPU).  Device-event time, max over ranks."""
     p = a.order
-    mesh = lpf.Mesh.wave_tank(128, 2, 16).refine(a.rk4_refine)
-    sp = lpf.Space(mesh, p)
+    mesh = lpf.Mesh.wave_tank(128 * world, 2, 16, Lx=1.0 * world).refine(a.rk4_refine)
+    sp = lpf.Space(mesh, p, nranks=world, rank=rank)
     ctx = lpf.Context(sp, device=local, stream=stream)
+    if world > 1 and a.comm == "p2p":
+        ctx.p2p_connect(dist)
+    elif world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        ctx.comm_init(bytes(idt.cpu().numpy().tobytes()))
     ctx.pa_setup()
     ctx.jacobi_setup()
     w = lpf.wave_params()
@@ -285,9 +295,15 @@ def rk4_measure(lpf, torch, a, local, stream):
     xs, ys = sp.surf_xy[:, 0], sp.surf_xy[:, 1]
     ph = -w["k"] * (w["kx_dir"] * xs + w["ky_dir"] * ys)
     st = np.concatenate([0.5 * w["H"] * np.cos(ph), -0.5 * w["H"] * w["cwave"] / np.tanh(w["kh"]) * np.sin(ph)])
-    sd = torch.from_numpy(st).cuda()
+    sd = torch.from_numpy(st).cuda() if len(st) else torch.zeros(2, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     t = ctx.rk4_step(sd, 0.0, dt)               # warm-up step (ss.cpp:253)
-    torch.cuda.synchronize()
+    barrier()
     l0 = ctx.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     nst = 2
@@ -295,13 +311,29 @@ def rk4_measure(lpf, torch, a, local, stream):
     for _ in range(nst):
         t = ctx.rk4_step(sd, t, dt)
     ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / nst
+    barrier()
+    tm = torch.tensor([ev0.elapsed_time(ev1) / nst], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm[0])
     infos = ctx.last_solve_info()
     its = [i.iterations for i in infos]
-    out = {"workload": f"wave-tank-big8 r={a.rk4_refine} order={p} ({sp.ne} hexes, {sp.ndof} dofs), RK4 dt=T/150, Jacobi-PCG rel 1e-12",
+    launches_per_step = int((ctx.launches - l0) / nst)
+    # the same step through the host-buffer entry point (H2D of the surface state + step + D2H), wall clock
+    hs = torch.from_numpy(np.ascontiguousarray(sd.cpu().numpy()[:max(2, len(st))])).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    ctx.rk4_step_host(hs, t, dt)
+    barrier()
+    th = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+    out = {"workload": f"wave-tank-big8 x{world} r={a.rk4_refine} order={p} ({sp.ne} hexes per GPU, {int(sp.n_true_global)} dofs), RK4 dt=T/150, Jacobi-PCG rel 1e-12",
            "ms_per_rk4_step": ms, "cg_iterations_per_stage": its, "converged": [int(i.converged) for i in infos],
-           "ms_per_cg_iteration": ms / max(1, sum(its)), "gpu_launches_per_step": int((ctx.launches - l0) / nst)}
+           "ms_per_cg_iteration": ms / max(1, sum(its)), "gpu_launches_per_step": launches_per_step,
+           "ms_per_rk4_step_host_api": float(th[0]), "h2d_d2h_bytes_per_step": int(16 * len(st))}
+    if world > 1:
+        out["p2p_flag_timeouts"] = int(ctx.p2p_error()) if a.comm == "p2p" else None
     ctx.close()
     return out
 

@@ -113,6 +113,26 @@ typedef struct {
 } lpf_space_desc;
 
 int lpf_space_desc_get(const lpf_space *s, lpf_space_desc *out);   /* pointers stay owned by `s` */
+/* f1  cylinder rim on the free surface (Solvers/cylinder-diffraction.cpp:449-505): the mesh VERTICES that lie on
+ * a boundary face of attribute wall_attr AND on the free surface, with |r - a| <= tol around (cx, cy) and
+ * theta = atan2(dy, dx) >= 0.  Writes up to `cap` (local surface dof, theta) pairs of this rank, returns the
+ * number found (or < 0 on error).  The caller gathers the ranks, sorts by theta and drops duplicates. */
+int lpf_space_rim(const lpf_space *s, int wall_attr, double cx, double cy, double a, double tol,
+                  int *surf_idx, double *theta, int cap);
+/* f2  MacCamy-Fuchs linear diffraction by a vertical circular cylinder: |eta|_max / (H/2) at (r >= a, phi), phi
+ * measured from the direction of propagation; the series of Solvers/cylinder-exact.cpp:53-115 (tol 1e-10, <= 400
+ * terms there) with std::cyl_bessel_j / std::cyl_neumann in place of Boost.Math. */
+double lpf_maccamy_fuchs(double k, double a, double r, double phi, double tol, int max_iter);
+/* f3  free-surface faces of this rank as order-p quads: conn[nf][(p+1)^2] local surface dofs, lexicographic in the
+ * face's own axes (what ParaViewDataCollection writes for mesh_fs, :453-467).  conn = NULL: returns the count. */
+int lpf_space_surface_quads(const lpf_space *s, int *conn, int cap_faces);
+/* f3  one piece of the ParaView output of the free-surface fields (what pv_fs.Save() writes per rank and cycle,
+ * Solvers/PF_linear_par_partial.cpp:453-467,505-514): an ASCII .vtu with the faces as
+ * VTK_LAGRANGE_QUADRILATERAL cells of order p (high_order = 1, SetHighOrderOutput(true)) or p*p bilinear sub-quads
+ * (0).  As in MFEM's writer every cell carries its own copy of its nodes (coordinates from the element geometry, so
+ * periodic seams are drawn correctly); nfields point-data arrays are sampled from fields[k][n_surf]. `z` is unused. */
+int lpf_write_surface_vtu(const lpf_space *s, const char *path, double z, int nfields, const char *const *names,
+                          const double *const *fields, int high_order);
 /* global (unpartitioned) node coordinates of the L-dofs of this rank: xyz[ndof][3] */
 int lpf_space_node_coordinates(const lpf_space *s, double *xyz_host);
 
@@ -196,12 +216,20 @@ typedef struct {
 } lpf_rhs_params;
 
 int lpf_rhs_setup(lpf_ctx *ctx, const lpf_rhs_params *prm, const double *cgen_host, const double *cabs_host);
+/* a14, cylinder driver: third relaxation weight C_absy (absorption towards y_max), added after C_abs in the
+ * same order as Solvers/cylinder-diffraction.cpp:199-210.  NULL switches it off again.  Call after lpf_rhs_setup. */
+int lpf_rhs_set_cabsy(lpf_ctx *ctx, const double *cabsy_host);
 /* a16  rhs_linear::Mult at stage time t: state = [eta ; phi_fs] (2 n_surf), dstate likewise (:130-244) */
 int lpf_rhs(lpf_ctx *ctx, double t, const double *state_dev, double *dstate_dev);
 /* a15  RK4Solver::Step(x, t, dt): advances state in place, *t += dt                  (:494) */
 int lpf_rk4_step(lpf_ctx *ctx, double *state_dev, double *t, double dt);
 /* same with HOST state (H2D + step + D2H inside) */
 int lpf_rk4_step_host(lpf_ctx *ctx, double *state_host, double *t, double dt);
+/* f1  eta envelope of Solvers/cylinder-diffraction.cpp:410-432: env = -1e300; env = max(env, eta) per step
+ * (state_dev = [eta ; phi_fs], device); _get copies it to the host and multiplies by `scale` (2/H, :444). */
+int lpf_envelope_reset(lpf_ctx *ctx);
+int lpf_envelope_update(lpf_ctx *ctx, const double *state_dev);
+int lpf_envelope_get(lpf_ctx *ctx, double *env_host, double scale);
 /* iteration counts of the (up to 4) solves of the last rhs / rk4 call */
 int lpf_last_solve_info(lpf_ctx *ctx, lpf_pcg_info info[4], int *nsolves);
 /* volume potential of the last solve (device pointer owned by the context, ndof doubles) */

@@ -91,6 +91,10 @@ SIGNATURES = {
     "lpf_basis_tables": (C.c_int, [C.c_int, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     "lpf_space_desc_get": (C.c_int, [_VP, C.POINTER(SpaceDesc)]),
     "lpf_space_node_coordinates": (C.c_int, [_VP, c_dp]),
+    "lpf_space_rim": (C.c_int, [_VP, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, c_ip, c_dp, C.c_int]),
+    "lpf_space_surface_quads": (C.c_int, [_VP, c_ip, C.c_int]),
+    "lpf_write_surface_vtu": (C.c_int, [_VP, C.c_char_p, C.c_double, C.c_int, C.POINTER(C.c_char_p), C.POINTER(c_dp), C.c_int]),
+    "lpf_maccamy_fuchs": (C.c_double, [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]),
     "lpf_create": (_VP, [C.POINTER(SpaceDesc), C.c_int, _VP]),
     "lpf_destroy": (None, [_VP]),
     "lpf_stream": (_VP, [_VP]),
@@ -115,6 +119,10 @@ SIGNATURES = {
     "lpf_laplace_solve": (C.c_int, [_VP, _VP, C.c_double, C.c_double, C.c_int, C.POINTER(PcgInfo)]),
     "lpf_surface_dz": (C.c_int, [_VP, _VP, _VP]),
     "lpf_rhs_setup": (C.c_int, [_VP, C.POINTER(RhsParams), c_dp, c_dp]),
+    "lpf_rhs_set_cabsy": (C.c_int, [_VP, c_dp]),
+    "lpf_envelope_reset": (C.c_int, [_VP]),
+    "lpf_envelope_update": (C.c_int, [_VP, _VP]),
+    "lpf_envelope_get": (C.c_int, [_VP, c_dp, C.c_double]),
     "lpf_rhs": (C.c_int, [_VP, C.c_double, _VP, _VP]),
     "lpf_rk4_step": (C.c_int, [_VP, _VP, c_dp, C.c_double]),
     "lpf_rk4_step_host": (C.c_int, [_VP, _VP, c_dp, C.c_double]),
@@ -298,6 +306,31 @@ class Space:
         self.desc = d
         return self
 
+    def rim(self, wall_attr=3, cx=4.0, cy=4.0, a=0.5, tol=5e-3):
+        """(theta, local surface dof) of the mesh vertices on the cylinder rim (cylinder-diffraction.cpp:476-496)."""
+        n = lib.lpf_space_rim(self.h, wall_attr, cx, cy, a, tol, None, None, 0)
+        if n < 0:
+            raise LpfError("lpf_space_rim: " + last_error())
+        idx, th = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1))
+        lib.lpf_space_rim(self.h, wall_attr, cx, cy, a, tol, idx.ctypes.data_as(c_ip), th.ctypes.data_as(c_dp), n)
+        return th[:n], idx[:n]
+
+    def surface_quads(self):
+        """[nf][(p+1)^2] local surface dofs of the free-surface faces (order-p quads, lexicographic)."""
+        nf = lib.lpf_space_surface_quads(self.h, None, 0)
+        if nf < 0:
+            raise LpfError("lpf_space_surface_quads: " + last_error())
+        conn = np.zeros((max(nf, 1), (self.order + 1) ** 2), np.int32)
+        lib.lpf_space_surface_quads(self.h, conn.ctypes.data_as(c_ip), nf)
+        return conn[:nf]
+
+    def write_surface_vtu(self, path, fields, z=0.0, high_order=True):
+        """One ParaView piece (.vtu) of the free-surface fields {name: array[n_surf]} (pv_fs.Save(), :505-514)."""
+        names = (C.c_char_p * max(1, len(fields)))(*[k.encode() for k in fields])
+        arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in fields.values()]
+        ptrs = (c_dp * max(1, len(fields)))(*[a.ctypes.data_as(c_dp) for a in arrs])
+        _check(lib.lpf_write_surface_vtu(self.h, str(path).encode(), float(z), len(fields), names, ptrs, int(high_order)), "lpf_write_surface_vtu")
+
     def node_coordinates(self):
         xyz = np.zeros((self.ndof, 3))
         if self.h is None:
@@ -412,6 +445,21 @@ class Context:
         _check(lib.lpf_rhs_setup(self.h, C.byref(prm), cg.ctypes.data_as(c_dp) if cg is not None else None,
                                  ca.ctypes.data_as(c_dp) if ca is not None else None), "lpf_rhs_setup")
 
+    def rhs_set_cabsy(self, cabsy):
+        ca = np.ascontiguousarray(cabsy, dtype=np.float64) if cabsy is not None else None
+        _check(lib.lpf_rhs_set_cabsy(self.h, ca.ctypes.data_as(c_dp) if ca is not None else None), "lpf_rhs_set_cabsy")
+
+    def envelope_reset(self):
+        _check(lib.lpf_envelope_reset(self.h), "lpf_envelope_reset")
+
+    def envelope_update(self, state):
+        _check(lib.lpf_envelope_update(self.h, _ptr(state)), "lpf_envelope_update")
+
+    def envelope_get(self, scale=1.0):
+        env = np.zeros(max(1, lib.lpf_nsurf(self.h)))
+        _check(lib.lpf_envelope_get(self.h, env.ctypes.data_as(c_dp), float(scale)), "lpf_envelope_get")
+        return env[:lib.lpf_nsurf(self.h)]
+
     def rhs(self, t, state, dstate):
         _check(lib.lpf_rhs(self.h, float(t), _ptr(state), _ptr(dstate)), "lpf_rhs")
 
@@ -462,6 +510,13 @@ def _hostptr(a):
         return a.ctypes.data
     assert not a.is_cuda and a.is_contiguous() and a.element_size() == 8
     return a.data_ptr()
+
+
+def maccamy_fuchs(k, a, r, phi, tol=1e-10, max_iter=400):
+    """MacCamy-Fuchs envelope |eta|_max / (H/2) (cylinder-exact.cpp:53-115) through the C-ABI."""
+    r, phi = np.broadcast_arrays(np.asarray(r, dtype=np.float64), np.asarray(phi, dtype=np.float64))
+    return np.array([lib.lpf_maccamy_fuchs(float(k), float(a), float(ri), float(pi), float(tol), int(max_iter))
+                     for ri, pi in zip(r.ravel(), phi.ravel())]).reshape(r.shape)
 
 
 def comm_unique_id() -> bytes:

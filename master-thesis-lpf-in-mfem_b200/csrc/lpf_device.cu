@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,6 +50,19 @@ int upload(T *&dst, const T *src, size_t n, size_t *bytes)
     return LPF_OK;
 }
 
+// Kernel launch with (optionally) the programmatic-dependent-launch attribute; see griddep_wait() in vec_kernels.cuh.
+template <class... KArgs, class... Args>
+cudaError_t launch_ex(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 inline int vec_grid(int n, int sm_count)
 {
     const int need = (n + 255) / 256;
@@ -70,6 +84,8 @@ struct lpf_ctx {
     // options
     int variant = 0;          // apply kernel variant (elements per CTA / prefetch), see apply_launch
     int use_graph = 1, chunk = 16, skip_zero_apply = 1;
+    int pdl = 1;              // programmatic dependent launch between the kernels of a PCG iteration
+    bool pdl_now = false;     // set while pcg_iteration() enqueues
     int max_ctas = 0;
     int ess_general = 0;      // lpf_pcg: search directions may be non-zero on essential dofs
     // geometry / maps
@@ -84,7 +100,8 @@ struct lpf_ctx {
     int *bad = nullptr;
     // surface
     int *surf2vol = nullptr, *surf_mult = nullptr, *sd_off = nullptr, *sd_elem = nullptr, *sd_node = nullptr;
-    double *surf_xy = nullptr, *cgen = nullptr, *cabs = nullptr, *wsum = nullptr;
+    double *surf_xy = nullptr, *cgen = nullptr, *cabs = nullptr, *cabsy = nullptr, *env = nullptr, *wsum = nullptr;
+    bool use_cabsy = false;
     double *rk_k = nullptr, *rk_y = nullptr, *rk_z = nullptr, *state_dev = nullptr;
     double *state_pinned = nullptr;
     RhsDev rhs{};
@@ -183,8 +200,7 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
     const int nb = (c->ne + E - 1) / E;
     if (nb == 0) return LPF_OK;
     const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
-    if (den) kd<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status, c->tail);
-    else kn<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status, c->tail);
+    CUDA_TRY(launch_ex(c->pdl_now, den ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c->stream, c->qd, gmap, x, y, c->ne, den, status, c->tail));
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
@@ -416,6 +432,8 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (stream) c->stream = (cudaStream_t)stream;
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    if (const char *e = std::getenv("LPF_PDL")) c->pdl = std::atoi(e);          // A/B switches for the drivers
+    if (const char *e = std::getenv("LPF_PCG_CHUNK")) c->chunk = std::max(1, std::atoi(e));
     c->p = d->order; c->D = d->order + 1; c->Q = d->order + 2;
     c->ne = d->ne; c->ndof = d->ndof; c->ness = d->n_ess; c->nsurf = d->n_surf;
     c->nranks = d->nranks > 0 ? d->nranks : 1; c->rank = d->rank;
@@ -544,6 +562,8 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         LPF_TRY(upload(c->wsum, (const double *)nullptr, ns, &c->bytes));
         LPF_TRY(upload(c->cgen, (const double *)nullptr, ns, &c->bytes));
         LPF_TRY(upload(c->cabs, (const double *)nullptr, ns, &c->bytes));
+        LPF_TRY(upload(c->cabsy, (const double *)nullptr, ns, &c->bytes));
+        LPF_TRY(upload(c->env, (const double *)nullptr, ns, &c->bytes));
         LPF_TRY(upload(c->rk_k, (const double *)nullptr, 2 * ns, &c->bytes));
         LPF_TRY(upload(c->rk_y, (const double *)nullptr, 2 * ns, &c->bytes));
         LPF_TRY(upload(c->rk_z, (const double *)nullptr, 2 * ns, &c->bytes));
@@ -587,7 +607,7 @@ void lpf_destroy(lpf_ctx *c)
     c->comm.destroy();
     void *ptrs[] = {c->corners, c->jac, c->jinv_z, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
                     c->z, c->d, c->ad, c->X, c->Bv, c->tmp, c->den_slots, c->partials, c->st, c->bad, c->surf2vol,
-                    c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->wsum, c->rk_k,
+                    c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->cabsy, c->env, c->wsum, c->rk_k,
                     c->rk_y, c->rk_z, c->state_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     free_halo(c->halo); free_halo(c->shalo);
@@ -625,6 +645,7 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "pcg_chunk") { if (value < 1) { lpf::set_error("pcg_chunk must be >= 1"); return LPF_ERR_ARG; } c->chunk = (int)value; }
     else if (k == "skip_zero_apply") c->skip_zero_apply = (int)value;
     else if (k == "p2p_fuse") c->p2p_fuse = (int)value;
+    else if (k == "pdl") c->pdl = (int)value;
     else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
     if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
@@ -840,25 +861,39 @@ int pcg_iteration(lpf_ctx *c)
 {
     const int n = c->ndof, g = vec_grid(n, c->sm_count);
     const bool multi = c->nranks > 1;
+    const uint8_t *no_mask = nullptr;
+    const bool tma_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
     if (p2p_fused(c)) {
         // three launches, as on one GPU: the betanom all-reduce runs in the last block of the update kernel, the
         // halo-sum and the (d, A d) all-reduce in the last CTA of the apply kernel (peer-memory stores + flags)
-        pcg_update_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->partials, c->p2p);
-        pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
+        const bool pdl = c->pdl != 0;
+        CUDA_TRY(launch_ex(pdl, pcg_update_p2p_kernel, dim3(g), dim3(256), 0, c->stream, n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->partials, c->p2p));
+        CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
         c->launches += 2;
-        return apply_with_tail(c, c->d, c->ad);
+        c->pdl_now = pdl;
+        const int rc = apply_with_tail(c, c->d, c->ad);
+        c->pdl_now = false;
+        return rc;
     }
     if (multi) {
         pcg_update_kernel<true><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->den_slots, c->partials);
         c->launches++;
         LPF_TRY(multi_reduce(c, P2P_RED_BETA));
-    } else {
-        pcg_update_kernel<false><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, nullptr, c->st, c->den_slots, c->partials);
+        pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
         c->launches++;
+        LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+    } else {
+        // single GPU: update -> direction -> apply chained by programmatic dependent launches (the ess_fix kernel of
+        // general right-hand sides has no griddep_wait, so that path keeps plain stream order)
+        const bool pdl = c->pdl != 0 && tma_kernel && !c->ess_general;
+        CUDA_TRY(launch_ex(pdl, pcg_update_kernel<false>, dim3(g), dim3(256), 0, c->stream, n, c->X, c->r, c->z, c->d, c->ad, c->dinv, no_mask, c->st, c->den_slots, c->partials));
+        CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
+        c->launches += 2;
+        c->pdl_now = pdl;
+        const int rc = apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status);
+        c->pdl_now = false;
+        LPF_TRY(rc);
     }
-    pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
-    c->launches++;
-    LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
     LPF_TRY(ess_fix(c));
     if (multi) {
         LPF_TRY(halo_sum(c, c->halo, c->ad));
@@ -1040,7 +1075,53 @@ int lpf_rhs_setup(lpf_ctx *c, const lpf_rhs_params *p, const double *cgen, const
         CUDA_TRY(cudaMemcpyAsync(c->cabs, cabs, sizeof(double) * c->nsurf, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
+    c->use_cabsy = false;
     c->rhs_done = true;
+    return LPF_OK;
+}
+
+int lpf_rhs_set_cabsy(lpf_ctx *c, const double *cabsy)
+{
+    if (!c) { lpf::set_error("lpf_rhs_set_cabsy: null context"); return LPF_ERR_ARG; }
+    if (!c->rhs_done) { lpf::set_error("lpf_rhs_set_cabsy before lpf_rhs_setup"); return LPF_ERR_STATE; }
+    c->use_cabsy = cabsy != nullptr;
+    if (cabsy && c->nsurf) {
+        CUDA_TRY(cudaMemcpyAsync(c->cabsy, cabsy, sizeof(double) * c->nsurf, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return LPF_OK;
+}
+
+int lpf_envelope_reset(lpf_ctx *c)
+{
+    if (!c) { lpf::set_error("lpf_envelope_reset: null context"); return LPF_ERR_ARG; }
+    if (c->nsurf) {
+        fill_kernel<<<(c->nsurf + 255) / 256, 256, 0, c->stream>>>(c->nsurf, -1e300, c->env);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LPF_OK;
+}
+
+int lpf_envelope_update(lpf_ctx *c, const double *state)
+{
+    if (!c || !state) { lpf::set_error("lpf_envelope_update: null argument"); return LPF_ERR_ARG; }
+    if (c->nsurf) {
+        envelope_kernel<<<(c->nsurf + 255) / 256, 256, 0, c->stream>>>(c->nsurf, state, c->env);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LPF_OK;
+}
+
+int lpf_envelope_get(lpf_ctx *c, double *env_host, double scale)
+{
+    if (!c || !env_host) { lpf::set_error("lpf_envelope_get: null argument"); return LPF_ERR_ARG; }
+    if (c->nsurf) {
+        CUDA_TRY(cudaMemcpyAsync(env_host, c->env, sizeof(double) * c->nsurf, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < c->nsurf; i++) env_host[i] *= scale;
+    }
     return LPF_OK;
 }
 
@@ -1058,7 +1139,8 @@ static int rhs_impl(lpf_ctx *c, double t, const double *state, double *dstate, l
         surface_dz_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(c->p, ns, c->sd_off, c->sd_elem, c->sd_node, c->gmap, c->corners, c->jinv_z, c->X, c->wsum);
         c->launches++;
         LPF_TRY(halo_sum(c, c->shalo, c->wsum));
-        surface_rhs_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(ns, c->rhs, t, c->surf_mult, c->wsum, state, c->surf_xy, c->cgen, c->cabs, dstate);
+        surface_rhs_kernel<<<(ns + 127) / 128, 128, 0, c->stream>>>(ns, c->rhs, t, c->surf_mult, c->wsum, state, c->surf_xy, c->cgen, c->cabs,
+                                                                        c->use_cabsy ? c->cabsy : nullptr, dstate);
         c->launches++;
     }
     CUDA_TRY(cudaGetLastError());

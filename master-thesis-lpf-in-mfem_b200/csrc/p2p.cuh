@@ -262,6 +262,8 @@ __global__ void pcg_update_p2p_kernel(int n, double *__restrict__ x, double *__r
                                       const double *__restrict__ dinv, const uint8_t *__restrict__ owned, PcgState *st,
                                       double *partials, P2PDev pd)
 {
+    griddep_wait();
+    griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
     if (st->status != PCG_RUNNING) return;
     const double den = st->red[1];                  // all-reduced by the tail of the previous apply
     if (den == 0.0) {

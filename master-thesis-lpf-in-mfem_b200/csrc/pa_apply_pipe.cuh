@@ -196,7 +196,7 @@ pa_apply_pipe_kernel(const double *__restrict__ qd, const int *__restrict__ gmap
 #pragma unroll
                 for (int q = 0; q < Q; q++) { s = fma(T.BG[2 * (q * D + i)], ta[q], s); s = fma(T.BG[2 * (q * D + i) + 1], tb[q], s); }
                 if (idx[i] >= 0) {
-                    atomicAdd(y + idx[i], s);
+                    red_add_f64(y + idx[i], s);
                     if (DEN) part = fma(xs[i], s, part);
                 }
             }

@@ -71,7 +71,6 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
     constexpr int DP3 = C::DP3, QE = C::QE;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (status != nullptr && *status != 0) return;
     double *sq = reinterpret_cast<double *>(smem_raw + C::OFF_Q);
     int *sidx = reinterpret_cast<int *>(smem_raw + C::OFF_IDX);
     double *smem = reinterpret_cast<double *>(smem_raw + C::OFF_WORK);
@@ -105,6 +104,15 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
         bulk_g2s(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i);
         mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
         bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+    }
+    // Everything above touches only constant data (gather map, q-data): under programmatic dependent launch it overlaps
+    // the tail of the previous kernel.  x, y and the PCG status are produced by that kernel: wait for it here.
+    griddep_wait();
+    griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
+    if (status != nullptr && *status != 0) {      // solve already finished: drain the copies issued above and leave
+        mbar_wait(bar_i, 0);
+        mbar_wait(bar_q, 0);
+        return;
     }
     double xs[D], xsn[D];
     double part = 0.0;
@@ -270,7 +278,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
                 for (int q = 0; q < Q; q++) { const double2 c = BGL(q, i); s = fma(c.x, ta[q], s); s = fma(c.y, tb[q], s); }
                 const int g = gi[i];
                 if (g >= 0) {
-                    atomicAdd(y + g, s);
+                    red_add_f64(y + g, s);
                     if (DEN) part = fma(xs[i], s, part);
                 }
             }

@@ -23,6 +23,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Scatter-add without a return value: always the fire-and-forget reduction (SASS REDG), never the round-trip ATOMG.
+// (With plain atomicAdd the compiler switched to ATOMG as soon as the kernel also read y elsewhere -- the fused
+// halo tail -- which cost 30 % of the apply kernel's bandwidth; profiles/r01_apply_ncu.md.)
+__device__ __forceinline__ void red_add_f64(double *addr, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
 #define LPF_MAXP 8
 
 struct __align__(16) LpfBasisTab {
@@ -238,7 +246,7 @@ pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, con
 #pragma unroll
             for (int q = 0; q < Q; q++) { s = fma(T.BG[2 * (q * D + i)], ta[q], s); s = fma(T.BG[2 * (q * D + i) + 1], tb[q], s); }
             if (EVEC) dst[i] += s;
-            else if (idx[i] >= 0) { atomicAdd(y + idx[i], s); part = fma(xs[i], s, part); }
+            else if (idx[i] >= 0) { red_add_f64(y + idx[i], s); part = fma(xs[i], s, part); }
         }
     }
     if (den_slots != nullptr) {

@@ -8,6 +8,14 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; griddep_wait() blocks until the predecessor has
+// completed and its writes are visible, griddep_launch() lets the successor's CTAs be scheduled early.  Both are
+// no-ops for a kernel launched without the attribute.  Every kernel of the PCG iteration calls them, which hides
+// most of the 2-3 us launch + prologue latency between the three kernels of an iteration (small meshes are launch-bound).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 enum { PCG_RUNNING = 0, PCG_CONVERGED = 1, PCG_MAXITER = 2, PCG_BREAKDOWN = 3, PCG_NOT_PD = 4 };
 
 #define LPF_DEN_SLOTS 256
@@ -133,6 +141,8 @@ __global__ void pcg_update_kernel(int n, double *__restrict__ x, double *__restr
                                   const double *__restrict__ dinv, const uint8_t *__restrict__ owned, PcgState *st,
                                   const double *__restrict__ den_slots, double *partials)
 {
+    griddep_wait();
+    griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
     if (st->status != PCG_RUNNING) return;
     double den;
     if (MULTI) den = st->red[1];
@@ -160,6 +170,8 @@ __global__ void pcg_update_kernel(int n, double *__restrict__ x, double *__restr
 __global__ void pcg_dir_kernel(int n, const double *__restrict__ z, double *__restrict__ d, double *__restrict__ ad,
                                const PcgState *st, double *den_slots)
 {
+    griddep_wait();
+    griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
     if (st->status != PCG_RUNNING) return;
     const double beta = st->beta;
     if (blockIdx.x == 0 && threadIdx.x < LPF_DEN_SLOTS) den_slots[threadIdx.x] = 0.0;
@@ -286,7 +298,8 @@ struct RhsDev {
 __global__ void surface_rhs_kernel(int ns, RhsDev prm, double t, const int *__restrict__ mult,
                                    const double *__restrict__ wsum, const double *__restrict__ state,
                                    const double *__restrict__ xy, const double *__restrict__ cgen,
-                                   const double *__restrict__ cabs, double *__restrict__ dstate)
+                                   const double *__restrict__ cabs, const double *__restrict__ cabsy,
+                                   double *__restrict__ dstate)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= ns) return;
@@ -304,9 +317,25 @@ __global__ void surface_rhs_kernel(int ns, RhsDev prm, double t, const int *__re
         dphi += (gw * prm.inv_tau) * (phi_e - pfs);
         deta += (cabs[s] * prm.inv_tau) * (0.0 - eta);
         dphi += (cabs[s] * prm.inv_tau) * (0.0 - pfs);
+        if (cabsy != nullptr) {       // third weight of the cylinder driver (cylinder-diffraction.cpp:199-210), same order of adds
+            deta += (cabsy[s] * prm.inv_tau) * (0.0 - eta);
+            dphi += (cabsy[s] * prm.inv_tau) * (0.0 - pfs);
+        }
     }
     dstate[s] = deta;
     dstate[ns + s] = dphi;
+}
+
+// eta envelope: env = max(env, eta) over the steps of the last period (cylinder-diffraction.cpp:410-432)
+__global__ void envelope_kernel(int ns, const double *__restrict__ state, double *__restrict__ env)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < ns) env[s] = fmax(env[s], state[s]);
+}
+__global__ void fill_kernel(int n, double v, double *__restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
 }
 
 // RK4Solver::Step vector updates ([MFEM] linalg/ode.cpp), stage = 0..3

@@ -21,7 +21,7 @@ int main(int argc, char *argv[])
         const int ref_levels = a.geti("--ref", 0);
         const int num_procs = a.geti("--gpus", 1);
         const bool relax = !a.has("--no-relax");
-        const std::string mesh_file = a.get("--mesh", cyl ? "../../tests/meshes/cylinder_half.mesh" : "wave-tank-finite.mesh");
+        const std::string mesh_file = a.get("--mesh", cyl ? "../../../tests/meshes/cylinder_half.mesh" : "wave-tank-finite.mesh");
         std::unique_ptr<Mesh> mesh(Mesh::FromName(mesh_file));
         for (int i = 0; i < ref_levels; i++) mesh->UniformRefinement();
 
@@ -67,6 +67,15 @@ int main(int argc, char *argv[])
             surface.Setup(w.params(dt, relax, 1e-12, cyl ? 2000 : 1000), cgen.data(), cabs.data());   // :157-164, tau = dt :470
             surface.SetState(state);
             std::vector<double> env(ns, -1e300);
+            // ParaView output of eta / phi_fs every 5 steps (:453-467, 505-514); off unless --paraview <name> is given
+            const std::string pv_name = a.get("--paraview", "");
+            std::vector<double> eta_host(ns), phi_host(ns);
+            ParaViewDataCollection pv_fs(pv_name, fespace, myid, num_procs, hi[2]);
+            pv_fs.SetPrefixPath("ParaView");
+            pv_fs.SetLevelsOfDetail(order);
+            pv_fs.SetHighOrderOutput(true);
+            pv_fs.RegisterField("eta", &eta_host);
+            pv_fs.RegisterField("phi_fs", &phi_host);
             double t = 0.0;
             const auto t0 = std::chrono::steady_clock::now();
             for (int step = 0; step < nsteps + 1; step++) {               // nsteps + 1 steps as in the reference (:492)
@@ -74,6 +83,12 @@ int main(int argc, char *argv[])
                 if (cyl && t >= t_last_start) {                            // eta envelope over the last period
                     surface.GetState(state);
                     for (int s = 0; s < ns; s++) env[s] = std::max(env[s], state[s]);
+                }
+                if (!pv_name.empty() && step % 5 == 0) {
+                    surface.GetState(state);
+                    std::copy(state.begin(), state.begin() + ns, eta_host.begin());
+                    std::copy(state.begin() + ns, state.end(), phi_host.begin());
+                    pv_fs.SetCycle(step); pv_fs.SetTime(t); pv_fs.Save();
                 }
                 if (myid == 0 && step % 10 == 0) {
                     auto it = surface.LastIterations();

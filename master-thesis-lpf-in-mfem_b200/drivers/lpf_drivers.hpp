@@ -85,6 +85,18 @@ public:
         check(lpf_space_node_coordinates(s_, xyz.data()), "node coordinates");
         return xyz;
     }
+    /// (theta, local surface dof) of the mesh vertices on the cylinder rim (cylinder-diffraction.cpp:476-496)
+    std::vector<std::pair<double, int>> Rim(int wall_attr, double cx, double cy, double a, double tol) const
+    {
+        const int n = lpf_space_rim(s_, wall_attr, cx, cy, a, tol, nullptr, nullptr, 0);
+        if (n < 0) throw std::runtime_error(lpf_last_error());
+        std::vector<int> idx(n); std::vector<double> th(n);
+        lpf_space_rim(s_, wall_attr, cx, cy, a, tol, idx.data(), th.data(), n);
+        std::vector<std::pair<double, int>> out;
+        for (int i = 0; i < n; i++) out.emplace_back(th[i], idx[i]);
+        return out;
+    }
+    lpf_space *handle() const { return s_; }
     lpf_space_desc desc{};
 private:
     lpf_space *s_;
@@ -183,6 +195,10 @@ public:
     ~RhsLinear() { lpf_dev_free(state_); lpf_destroy(ctx_); }
     RhsLinear(const RhsLinear &) = delete;
     void Setup(const lpf_rhs_params &p, const double *cgen, const double *cabs) { check(lpf_rhs_setup(ctx_, &p, cgen, cabs), "lpf_rhs_setup"); }
+    void SetCabsy(const double *cabsy) { check(lpf_rhs_set_cabsy(ctx_, cabsy), "lpf_rhs_set_cabsy"); }         // cylinder-diffraction.cpp:373-389
+    void EnvelopeReset() { check(lpf_envelope_reset(ctx_), "lpf_envelope_reset"); }                              // eta_env = -1e300  (:412)
+    void EnvelopeUpdate() { check(lpf_envelope_update(ctx_, state_), "lpf_envelope_update"); }                   // env = max(env, eta) (:421-430)
+    std::vector<double> Envelope(double scale) { std::vector<double> e((size_t)ns_); check(lpf_envelope_get(ctx_, e.data(), scale), "lpf_envelope_get"); return e; }
     void SetState(const std::vector<double> &s) { if (ns_) check(lpf_memcpy_h2d(state_, s.data(), sizeof(double) * 2 * ns_), "h2d"); }
     void GetState(std::vector<double> &s) { s.resize(2 * (size_t)ns_); check(lpf_sync(ctx_), "sync"); if (ns_) check(lpf_memcpy_d2h(s.data(), state_, sizeof(double) * 2 * ns_), "d2h"); }
     void Step(double &t, double dt) { check(lpf_rk4_step(ctx_, state_, &t, dt), "ode_solver->Step"); }   // :494
@@ -201,6 +217,53 @@ private:
     lpf_ctx *ctx_ = nullptr;
     double *state_ = nullptr;
     int ns_, ndof_;
+};
+
+// ---- mfem::ParaViewDataCollection for the free-surface fields (PF_linear_par_partial.cpp:453-467, 505-514) ----
+// <prefix>/<name>/Cycle000123/proc000000.vtu per rank and cycle + <prefix>/<name>/<name>.pvd listing every piece.
+class ParaViewDataCollection {
+public:
+    ParaViewDataCollection(const std::string &name, const RankSpace &fs, int rank, int nranks, double z)
+        : name_(name), fs_(fs), rank_(rank), nranks_(nranks), z_(z) {}
+    void SetPrefixPath(const std::string &p) { prefix_ = p; }
+    void SetLevelsOfDetail(int) {}                       // refinement of the VTK cells: the Lagrange cells carry order p already
+    void SetHighOrderOutput(bool h) { high_order_ = h; }
+    void RegisterField(const std::string &field, const std::vector<double> *values) { names_.push_back(field); fields_.push_back(values); }
+    void SetCycle(int c) { cycle_ = c; }
+    void SetTime(double t) { time_ = t; }
+    void Save()
+    {
+        char cyc[64];
+        snprintf(cyc, sizeof(cyc), "Cycle%06d", cycle_);
+        const std::string dir = prefix_ + "/" + name_ + "/" + cyc;
+        if (std::system(("mkdir -p '" + dir + "'").c_str()) != 0) throw std::runtime_error("cannot create " + dir);
+        char piece[64];
+        snprintf(piece, sizeof(piece), "proc%06d.vtu", rank_);
+        std::vector<const char *> nm;
+        std::vector<const double *> fl;
+        for (size_t k = 0; k < names_.size(); k++) { nm.push_back(names_[k].c_str()); fl.push_back(fields_[k]->data()); }
+        check(lpf_write_surface_vtu(fs_.handle(), (dir + "/" + piece).c_str(), z_, (int)nm.size(), nm.data(), fl.data(), high_order_ ? 1 : 0), "pv.Save");
+        if (rank_ == 0) {
+            saved_.emplace_back(time_, std::string(cyc));
+            FILE *f = fopen((prefix_ + "/" + name_ + "/" + name_ + ".pvd").c_str(), "w");
+            if (!f) throw std::runtime_error("cannot write the .pvd file");
+            fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"Collection\" version=\"0.1\">\n<Collection>\n");
+            for (auto &sv : saved_)
+                for (int r = 0; r < nranks_; r++)
+                    fprintf(f, "<DataSet timestep=\"%.12g\" part=\"%d\" file=\"%s/proc%06d.vtu\"/>\n", sv.first, r, sv.second.c_str(), r);
+            fprintf(f, "</Collection>\n</VTKFile>\n");
+            fclose(f);
+        }
+    }
+private:
+    std::string name_, prefix_ = "ParaView";
+    const RankSpace &fs_;
+    int rank_, nranks_, cycle_ = 0;
+    double z_, time_ = 0.0;
+    bool high_order_ = true;
+    std::vector<std::string> names_;
+    std::vector<const std::vector<double> *> fields_;
+    std::vector<std::pair<double, std::string>> saved_;
 };
 
 }  // namespace lpfd

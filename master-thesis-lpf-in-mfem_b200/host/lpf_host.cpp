@@ -563,6 +563,7 @@ H1Space::H1Space(const Mesh &mesh, int order_, int ess_attr) : order(order_), D(
         auto it = fdof.find(face_key(q[0], q[1], q[2], q[3]));
         if (it == fdof.end()) throw std::runtime_error("H1Space: boundary face not found among element faces");
         const int es[2] = {it->second.e0, it->second.e1}, fs[2] = {it->second.f0, it->second.f1};
+        surf_faces.push_back(es[0]); surf_faces.push_back(fs[0]);
         for (int side = 0; side < 2; side++) {
             const int e = es[side], f = fs[side];
             if (e < 0) continue;

@@ -56,6 +56,7 @@ struct H1Space {
     std::vector<int> surf2vol;          // surface dof -> volume dof, first-appearance order
     std::vector<double> surf_xy;        // [ns][2] coordinates of surface dofs
     std::vector<int> surf_elems;        // elements that hold at least one surface dof
+    std::vector<int> surf_faces;        // [nf][2] (element, local face 2*axis+side) of the boundary faces carrying ess_attr
     H1Space() = default;
     H1Space(const Mesh &mesh, int order, int ess_attr = 2);
     void NodeCoordinates(const Mesh &mesh, std::vector<double> &xyz) const;   // [ndof][3]

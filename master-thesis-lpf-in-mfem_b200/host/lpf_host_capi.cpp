@@ -1,4 +1,8 @@
 // C-ABI of the host mini-FEM layer (include/lpf_b200.h, "Host mini-FEM" section).
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -157,6 +161,194 @@ int lpf_space_desc_get(const lpf_space *s, lpf_space_desc *d)
     d->n_surf_global = p.n_surf_global;
     d->l2g = p.l2g.data();
     d->surf_g = p.surf_g.data();
+    return LPF_OK;
+}
+
+// |eta|_max / (H/2) on r >= a at angle phi from the direction of propagation (cylinder-exact.cpp:53-115)
+double lpf_maccamy_fuchs(double k, double a, double r, double phi, double tol, int max_iter)
+{
+    using cd = std::complex<double>;
+    const double ka = k * a, kr = k * r;
+    const double J0P = -std::cyl_bessel_j(1.0, ka);
+    const cd H0P(-std::cyl_bessel_j(1.0, ka), -std::cyl_neumann(1.0, ka));
+    const cd H0r(std::cyl_bessel_j(0.0, kr), std::cyl_neumann(0.0, kr));
+    cd E = std::cyl_bessel_j(0.0, kr) - H0r * (J0P / H0P);
+    double oldterm = 1.0;
+    for (int m = 1; m <= max_iter; m++) {
+        const double JmP = 0.5 * (std::cyl_bessel_j(m - 1.0, ka) - std::cyl_bessel_j(m + 1.0, ka));
+        const cd HmP(JmP, 0.5 * (std::cyl_neumann(m - 1.0, ka) - std::cyl_neumann(m + 1.0, ka)));
+        if (std::abs(HmP) < 1e-14) continue;
+        const double Jmr = std::cyl_bessel_j((double)m, kr);
+        const cd Hmr(Jmr, std::cyl_neumann((double)m, kr));
+        const double ph = m * M_PI / 2.0;
+        const cd coef = 2.0 * cd(std::cos(ph), std::sin(ph)) * (Jmr - Hmr * (JmP / HmP));
+        const cd term = coef * std::cos(m * phi);
+        if (std::isnan(term.real())) break;
+        E += term;
+        // The reference stops when Re(term) of two consecutive terms is below tol (cylinder-exact.cpp:104-110); with the
+        // cos(m phi) factor inside, that fires at m = 1 for phi = pi/2 (cos = 0, oldterm = 0) and truncates the series to
+        // its m = 0 term.  We test the phi-independent coefficient instead: same values to ~tol wherever the reference's
+        // rule does not fire spuriously, and correct at phi = pi/2.
+        const double nextterm = std::abs(coef);
+        if (nextterm < tol && oldterm < tol) break;
+        oldterm = nextterm;
+    }
+    return std::abs(E);
+}
+
+int lpf_space_rim(const lpf_space *s, int wall_attr, double cx, double cy, double a, double tol,
+                  int *surf_idx, double *theta, int cap)
+{
+    if (!s || !s->mesh || (cap > 0 && (!surf_idx || !theta))) { lpf::set_error("lpf_space_rim: null argument"); return LPF_ERR_ARG; }
+    const lpf::Mesh &m = *s->mesh;
+    const lpf::Partition &p = s->part;
+    const int D = s->order + 1, D3 = D * D * D, P = s->order;
+    std::vector<uint8_t> on_wall((size_t)m.nv, 0);
+    for (int b = 0; b < m.nb(); b++)
+        if (m.bdr_attr[b] == wall_attr) for (int k = 0; k < 4; k++) on_wall[m.bdr[(size_t)b * 4 + k]] = 1;
+    std::vector<int> vol2surf(p.l2g.size(), -1);
+    for (size_t i = 0; i < p.surf2vol.size(); i++) vol2surf[p.surf2vol[i]] = (int)i;
+    std::vector<uint8_t> seen((size_t)m.nv, 0);
+    int n = 0;
+    for (size_t le = 0; le < p.elems.size(); le++) {
+        const int ge = p.elems[le];
+        for (int c = 0; c < 8; c++) {
+            const int v = m.elems[(size_t)ge * 8 + lpf::kLex2Mfem[c]];
+            if (!on_wall[v] || seen[v]) continue;
+            const int loc = ((c & 1) ? P : 0) + D * ((((c >> 1) & 1) ? P : 0) + D * (((c >> 2) & 1) ? P : 0));
+            const int si = vol2surf[p.gather[le * D3 + loc]];
+            if (si < 0) continue;                                   // wall vertex below the free surface
+            seen[v] = 1;
+            const double dx = p.corners[le * 24 + c * 3] - cx, dy = p.corners[le * 24 + c * 3 + 1] - cy;
+            if (std::fabs(std::sqrt(dx * dx + dy * dy) - a) > tol) continue;
+            const double th = std::atan2(dy, dx);
+            if (th < 0.0) continue;
+            if (n < cap) { surf_idx[n] = si; theta[n] = th; }
+            n++;
+        }
+    }
+    return n;
+}
+
+/* free-surface faces of this rank as high-order quads: conn[nf][D*D] local surface dofs (x-fastest lexicographic
+ * in the face's own (s,t) axes); returns nf (pass conn = NULL to size) */
+int lpf_space_surface_quads(const lpf_space *s, int *conn, int cap_faces)
+{
+    if (!s) { lpf::set_error("lpf_space_surface_quads: null argument"); return LPF_ERR_ARG; }
+    const lpf::Partition &p = s->part;
+    const int D = s->order + 1, D3 = D * D * D, P = s->order;
+    std::vector<int> g2l;
+    {
+        int gmax = -1;
+        for (int ge : p.elems) gmax = std::max(gmax, ge);
+        g2l.assign((size_t)gmax + 1, -1);
+        for (size_t le = 0; le < p.elems.size(); le++) g2l[p.elems[le]] = (int)le;
+    }
+    std::vector<int> vol2surf(p.l2g.size(), -1);
+    for (size_t i = 0; i < p.surf2vol.size(); i++) vol2surf[p.surf2vol[i]] = (int)i;
+    int nf = 0;
+    const std::vector<int> &sf = s->space.surf_faces;
+    for (size_t f = 0; f + 1 < sf.size(); f += 2) {
+        const int ge = sf[f], lf = sf[f + 1];
+        if (ge >= (int)g2l.size() || g2l[ge] < 0) continue;
+        const int le = g2l[ge], ax = lf / 2, fixed = (lf & 1) ? P : 0;
+        if (conn && nf < cap_faces) {
+            for (int t = 0; t < D; t++)
+                for (int q = 0; q < D; q++) {
+                    int i, j, k;
+                    if (ax == 0) { i = fixed; j = q; k = t; } else if (ax == 1) { i = q; j = fixed; k = t; } else { i = q; j = t; k = fixed; }
+                    conn[(size_t)nf * D * D + q + D * t] = vol2surf[p.gather[(size_t)le * D3 + i + D * (j + D * k)]];
+                }
+        }
+        nf++;
+    }
+    return nf;
+}
+
+/* VTK (>= 9) node order of an order-p Lagrange quadrilateral in terms of the lexicographic lattice (i + D j):
+ * 4 corners, then the edges (bottom, right, top, left; each in increasing coordinate), then the interior row by row */
+static void vtk_lagrange_quad_order(int p, std::vector<int> &ord)
+{
+    const int D = p + 1;
+    ord.clear();
+    ord.push_back(0); ord.push_back(p); ord.push_back(p + D * p); ord.push_back(D * p);
+    for (int i = 1; i < p; i++) ord.push_back(i);
+    for (int j = 1; j < p; j++) ord.push_back(p + D * j);
+    for (int i = 1; i < p; i++) ord.push_back(i + D * p);
+    for (int j = 1; j < p; j++) ord.push_back(D * j);
+    for (int j = 1; j < p; j++) for (int i = 1; i < p; i++) ord.push_back(i + D * j);
+}
+
+int lpf_write_surface_vtu(const lpf_space *s, const char *path, double z, int nfields, const char *const *names,
+                          const double *const *fields, int high_order)
+{
+    (void)z;
+    if (!s || !path || nfields < 0 || (nfields > 0 && (!names || !fields))) { lpf::set_error("lpf_write_surface_vtu: bad argument"); return LPF_ERR_ARG; }
+    const lpf::Partition &p = s->part;
+    const int P = s->order, D = P + 1, DD = D * D, D3 = D * DD;
+    std::vector<int> g2l;
+    {
+        int gmax = -1;
+        for (int ge : p.elems) gmax = std::max(gmax, ge);
+        g2l.assign((size_t)gmax + 1, -1);
+        for (size_t le = 0; le < p.elems.size(); le++) g2l[p.elems[le]] = (int)le;
+    }
+    std::vector<int> vol2surf(p.l2g.size(), -1);
+    for (size_t i = 0; i < p.surf2vol.size(); i++) vol2surf[p.surf2vol[i]] = (int)i;
+    // faces of this rank; like MFEM's ParaView writer every cell carries its own copy of its nodes (discontinuous
+    // points), taken from the ELEMENT geometry -- so cells across a periodic seam keep their true coordinates
+    lpf::Basis1D bs(P);
+    std::vector<double> pts;      // [nf][DD][3]
+    std::vector<int> sdof;        // [nf][DD] surface dof of each cell node
+    const std::vector<int> &sf = s->space.surf_faces;
+    for (size_t f = 0; f + 1 < sf.size(); f += 2) {
+        const int ge = sf[f], lf = sf[f + 1];
+        if (ge >= (int)g2l.size() || g2l[ge] < 0) continue;
+        const int le = g2l[ge], ax = lf / 2, fixed = (lf & 1) ? P : 0;
+        const double *Cn = &p.corners[(size_t)le * 24];
+        for (int t = 0; t < D; t++)
+            for (int q = 0; q < D; q++) {
+                int i, j, k;
+                if (ax == 0) { i = fixed; j = q; k = t; } else if (ax == 1) { i = q; j = fixed; k = t; } else { i = q; j = t; k = fixed; }
+                sdof.push_back(vol2surf[p.gather[(size_t)le * D3 + i + D * (j + D * k)]]);
+                const double x = bs.nodes[i], y = bs.nodes[j], zz = bs.nodes[k];
+                double pt[3] = {0, 0, 0};
+                for (int c = 0; c < 8; c++) {
+                    const double w = ((c & 1) ? x : 1 - x) * (((c >> 1) & 1) ? y : 1 - y) * (((c >> 2) & 1) ? zz : 1 - zz);
+                    for (int d = 0; d < 3; d++) pt[d] += w * Cn[c * 3 + d];
+                }
+                pts.insert(pts.end(), pt, pt + 3);
+            }
+    }
+    const int nf = (int)(sdof.size() / DD), npts = nf * DD;
+    FILE *f = fopen(path, "w");
+    if (!f) { lpf::set_error(std::string("lpf_write_surface_vtu: cannot open ") + path); return LPF_ERR_ARG; }
+    // high_order: one VTK_LAGRANGE_QUADRILATERAL (70) per face; otherwise p*p bilinear VTK_QUAD (9) sub-cells
+    const int ncell = high_order ? nf : nf * P * P, npc = high_order ? DD : 4;
+    fprintf(f, "<?xml version=\"1.0\"?>\n<VTKFile type=\"UnstructuredGrid\" version=\"2.2\" byte_order=\"LittleEndian\">\n<UnstructuredGrid>\n");
+    fprintf(f, "<Piece NumberOfPoints=\"%d\" NumberOfCells=\"%d\">\n<Points>\n<DataArray type=\"Float64\" NumberOfComponents=\"3\" format=\"ascii\">\n", npts, ncell);
+    for (int i = 0; i < npts; i++) fprintf(f, "%.17g %.17g %.17g\n", pts[3 * (size_t)i], pts[3 * (size_t)i + 1], pts[3 * (size_t)i + 2]);
+    fprintf(f, "</DataArray>\n</Points>\n<Cells>\n<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">\n");
+    std::vector<int> ord;
+    vtk_lagrange_quad_order(P, ord);
+    for (int q = 0; q < nf; q++) {
+        const int base = q * DD;
+        if (high_order) { for (int k = 0; k < DD; k++) fprintf(f, "%d ", base + ord[k]); fprintf(f, "\n"); }
+        else for (int j = 0; j < P; j++) for (int i = 0; i < P; i++)
+            fprintf(f, "%d %d %d %d\n", base + i + D * j, base + i + 1 + D * j, base + i + 1 + D * (j + 1), base + i + D * (j + 1));
+    }
+    fprintf(f, "</DataArray>\n<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">\n");
+    for (int q = 1; q <= ncell; q++) fprintf(f, "%d\n", q * npc);
+    fprintf(f, "</DataArray>\n<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">\n");
+    for (int q = 0; q < ncell; q++) fprintf(f, "%d\n", high_order ? 70 : 9);
+    fprintf(f, "</DataArray>\n</Cells>\n<PointData>\n");
+    for (int k = 0; k < nfields; k++) {
+        fprintf(f, "<DataArray type=\"Float64\" Name=\"%s\" NumberOfComponents=\"1\" format=\"ascii\">\n", names[k]);
+        for (int i = 0; i < npts; i++) fprintf(f, "%.17g\n", fields[k][sdof[i]]);
+        fprintf(f, "</DataArray>\n");
+    }
+    fprintf(f, "</PointData>\n</Piece>\n</UnstructuredGrid>\n</VTKFile>\n");
+    fclose(f);
     return LPF_OK;
 }
 

@@ -848,9 +848,10 @@ def relax_cabs(x, x0, x1, pw=5.0):
 @dataclass
 class Relax:
     cgen: np.ndarray
-    cabs: np.ndarray       # sum of all absorption weights (C_abs + C_absy, cylinder-diffraction.cpp:206-209)
+    cabs: np.ndarray       # C_abs (absorption towards x_max)
     tau: float
     n_ramp: float = 3.0
+    cabsy: np.ndarray | None = None   # third weight of the cylinder driver, added after C_abs (cylinder-diffraction.cpp:199-210)
 
 
 class RhsLinear:
@@ -905,6 +906,9 @@ class RhsLinear:
             dphi = dphi + (gw * inv_tau) * (phi_e - phi_fs)
             deta = deta + (rx.cabs * inv_tau) * (0.0 - eta)
             dphi = dphi + (rx.cabs * inv_tau) * (0.0 - phi_fs)
+            if rx.cabsy is not None:
+                deta = deta + (rx.cabsy * inv_tau) * (0.0 - eta)
+                dphi = dphi + (rx.cabsy * inv_tau) * (0.0 - phi_fs)
         return np.concatenate([deta, dphi])
 
 

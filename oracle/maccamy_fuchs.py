@@ -9,7 +9,36 @@ import numpy as np
 from scipy.special import jv, yv
 
 
+def envelope_reference_rule(k, a, r, phi, tol=1e-10, max_iter=400):
+    """Point-by-point, with the reference's stopping rule exactly as written (cylinder-exact.cpp:104-110): stop when
+    |Re(term)| of two consecutive terms is below tol, oldterm starting at 0.  NOTE the quirk this documents: at
+    phi = pi/2 the m = 1 term vanishes (cos(phi) = 0) and the series stops after its first term."""
+    r, phi = np.broadcast_arrays(np.asarray(r, dtype=np.float64), np.asarray(phi, dtype=np.float64))
+    out = np.zeros(r.shape)
+    ka = k * a
+    for idx in np.ndindex(r.shape):
+        kr, ph = k * r[idx], phi[idx]
+        E = jv(0, kr) - (jv(0, kr) + 1j * yv(0, kr)) * (-jv(1, ka) / complex(-jv(1, ka), -yv(1, ka)))
+        old = 0.0
+        for m in range(1, max_iter + 1):
+            Jmp = 0.5 * (jv(m - 1, ka) - jv(m + 1, ka))
+            Hmp = complex(Jmp, 0.5 * (yv(m - 1, ka) - yv(m + 1, ka)))
+            if abs(Hmp) < 1e-14:
+                continue
+            term = 2.0 * np.exp(1j * m * np.pi / 2.0) * (jv(m, kr) - (jv(m, kr) + 1j * yv(m, kr)) * (Jmp / Hmp)) * np.cos(m * ph)
+            nxt = term.real
+            if np.isnan(nxt):
+                break
+            E += term
+            if abs(nxt) < tol and abs(old) < tol:
+                break
+            old = nxt
+        out[idx] = abs(E)
+    return out
+
+
 def envelope(k, a, r, phi, tol=1e-10, max_iter=400):
+    """Vectorised series; stops when the terms are below tol at ALL points (robust form of the rule above)."""
     r = np.asarray(r, dtype=np.float64)
     phi = np.asarray(phi, dtype=np.float64)
     ka, kr = k * a, k * r

@@ -303,6 +303,55 @@ def test_rhs_and_rk4_match_oracle(lpf, orc, cuda, tank, relax):
     ctx.close()
 
 
+def test_cylinder_rhs_third_weight_and_envelope(lpf, orc, cuda):
+    """cylinder-diffraction.cpp: RHS with C_gen, C_abs and C_absy on the unstructured half-cylinder mesh, the eta
+    envelope (max over steps, scaled by 2/H) and the rim sampling of it."""
+    torch = cuda
+    p = 2
+    m = lpf.Mesh.read(os.path.join(HERE, "meshes", "cylinder_half.mesh"))
+    sp = lpf.Space(m, p)
+    osp = oracle_space_from(orc, sp)
+    wv, st0 = _initial_state(orc, sp)
+    dt = wv.T / 35
+    lo, hi = m.bounding_box()
+    xs, ys = sp.surf_xy[:, 0], sp.surf_xy[:, 1]
+    cgen = orc.relax_cgen(xs, lo[0], lo[0] + 2.5)
+    cabs = orc.relax_cabs(xs, hi[0] - 4.0, hi[0])
+    cabsy = orc.relax_cabs(ys, hi[1] - 3.0, hi[1])
+    assert cabsy.max() == 1.0 and (cabsy > 0).sum() > 10
+    f = orc.RhsLinear(osp, wv, rel_tol=1e-12, max_iter=2000, relax=orc.Relax(cgen, cabs, tau=dt, cabsy=cabsy))
+    ctx = _ctx(lpf, torch, sp)
+    ctx.jacobi_setup()
+    ctx.rhs_setup(lpf.make_rhs_params(lpf.wave_params(), tau=dt, use_relaxation=True, rel_tol=1e-12, max_iter=2000), cgen, cabs)
+    ctx.rhs_set_cabsy(cabsy)
+    ns = sp.nsurf
+    f.set_time(0.21)
+    ko = f.mult(st0)
+    sd, kd = _dev(torch, st0), torch.empty(2 * ns, dtype=torch.float64, device="cuda")
+    ctx.rhs(0.21, sd, kd)
+    assert rel_err(kd.cpu().numpy()[:ns], ko[:ns]) < TOL_SOL and rel_err(kd.cpu().numpy()[ns:], ko[ns:]) < TOL_SOL
+    # without the third weight the RHS differs where C_absy > 0 -- the term is really applied
+    ctx.rhs_set_cabsy(None)
+    ctx.rhs(0.21, sd, kd)
+    assert rel_err(kd.cpu().numpy()[:ns], ko[:ns]) > 1e-6
+    ctx.rhs_set_cabsy(cabsy)
+    # one RK4 step with the envelope (the numpy oracle needs ~9 s per solve on this mesh)
+    ctx.envelope_reset()
+    so, to, tg = st0.copy(), 0.0, 0.0
+    env = np.full(ns, -1e300)
+    for _ in range(1):
+        so, to = orc.rk4_step(f, so, to, dt)
+        tg = ctx.rk4_step(sd, tg, dt)
+        env = np.maximum(env, so[:ns])
+        ctx.envelope_update(sd)
+    assert rel_err(sd.cpu().numpy(), so) < TOL_SOL
+    eg = ctx.envelope_get(2.0 / wv.H)
+    assert rel_err(eg, env * (2.0 / wv.H)) < TOL_SOL
+    th, idx = sp.rim()
+    assert len(th) >= 8 and np.all(np.isfinite(eg[idx]))
+    ctx.close()
+
+
 def test_golden_vectors(lpf, cuda):
     """Committed oracle outputs (tests/golden/tank_p3.npz, made by make_golden.py) through the
     arrays-only descriptor route an MFEM adapter would take."""

@@ -256,3 +256,83 @@ def test_two_rank_halo_sum_reproduces_serial_operator(lpf, orc):
     shared = set(copies[0]) & set(copies[1])
     assert len(shared) > 0
     assert all(copies[0][g] == copies[1][g] for g in shared)     # bit-identical copies on both sharers
+
+
+@pytest.mark.parametrize("nranks", [1, 3])
+def test_cylinder_rim_extraction(lpf, nranks):
+    """cylinder-diffraction.cpp:449-505: vertices shared by the wall (attr 3) and the free surface (attr 2), r = a,
+    theta = atan2 >= 0; gathered over the ranks, sorted, duplicates dropped."""
+    m = lpf.Mesh.read(os.path.join(HERE, "meshes", "cylinder_half.mesh"))
+    bdr, attr = m.boundary()
+    wall = set(bdr[attr == 3].reshape(-1).tolist()) & set(bdr[attr == 2].reshape(-1).tolist())
+    pts = []
+    for r in range(nranks):
+        sp = lpf.Space(m, 2, nranks=nranks, rank=r)
+        th, idx = sp.rim(3, 4.0, 4.0, 0.5, 5e-3)
+        assert np.all(th >= 0) and np.all(th <= np.pi + 1e-12)
+        if len(th) == 0:                       # a part may hold no rim vertex at all
+            continue
+        xy = sp.surf_xy[idx]
+        assert np.abs(np.hypot(xy[:, 0] - 4.0, xy[:, 1] - 4.0) - 0.5).max() < 5e-3
+        assert np.allclose(np.arctan2(xy[:, 1] - 4.0, xy[:, 0] - 4.0), th)
+        pts += list(th)
+    th = np.sort(np.array(pts))
+    th = th[np.concatenate([[True], np.diff(th) > 1e-10])]
+    assert len(th) == len(wall) >= 8           # every wall/free-surface vertex of the half cylinder, once
+    assert th[0] < 1e-9 and abs(th[-1] - np.pi) < 1e-9
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_surface_quads_cover_the_surface_space(lpf, nranks):
+    m = lpf.Mesh.wave_tank(8, 2, 2)
+    p = 3
+    nf = 0
+    for r in range(nranks):
+        sp = lpf.Space(m, p, nranks=nranks, rank=r)
+        q = sp.surface_quads()
+        nf += len(q)
+        assert q.shape[1] == (p + 1) ** 2 and q.min() >= 0 and q.max() < sp.nsurf
+        assert set(q.reshape(-1).tolist()) == set(range(sp.nsurf))
+        # each quad is a tensor lattice: its nodes sit on the GLL points of its bounding rectangle
+        xy = sp.surf_xy[q]                               # [nf][D*D][2]
+        t = lpf.basis_tables(p)["nodes"]
+        for f in range(len(q)):
+            lo, hi = xy[f].min(axis=0), xy[f].max(axis=0)
+            ex = lo[0] + (hi[0] - lo[0]) * t
+            assert np.allclose(np.sort(np.unique(np.round(xy[f][:, 0], 12))), np.round(ex, 12), atol=1e-10) or hi[0] - lo[0] > 0.5
+    assert nf == 16
+
+
+def test_surface_vtu_writer(lpf, tmp_path):
+    """f3: ParaView piece of the free-surface fields: Lagrange quads of order p in VTK node order, point data;
+    cells own their nodes, so the periodic seam cell keeps its true coordinates."""
+    import xml.etree.ElementTree as ET
+    m = lpf.Mesh.wave_tank(4, 2, 2)
+    for p, ho in ((3, True), (2, False)):
+        sp = lpf.Space(m, p)
+        eta = np.cos(2 * np.pi * sp.surf_xy[:, 0])
+        path = tmp_path / f"s{p}.vtu"
+        sp.write_surface_vtu(path, {"eta": eta, "phi_fs": 2 * eta}, high_order=ho)
+        piece = ET.parse(path).getroot().find("UnstructuredGrid/Piece")
+        ncell = 8 if ho else 8 * p * p
+        assert int(piece.get("NumberOfPoints")) == 8 * (p + 1) ** 2 and int(piece.get("NumberOfCells")) == ncell
+        pts = np.array(piece.find("Points/DataArray").text.split(), dtype=float).reshape(-1, 3)
+        assert np.allclose(pts[:, 2], H) and pts[:, 0].max() == 1.0 and pts[:, 0].min() == 0.0
+        arr = {d.get("Name"): d for d in piece.findall("Cells/DataArray")}
+        conn = np.array(arr["connectivity"].text.split(), dtype=int).reshape(ncell, -1)
+        types = np.array(arr["types"].text.split(), dtype=int)
+        assert np.all(types == (70 if ho else 9)) and conn.shape[1] == ((p + 1) ** 2 if ho else 4)
+        c = pts[conn[:, :4], :2]                       # the first four nodes of a cell are its corners, in cyclic order
+        assert np.allclose(c[:, 0] + c[:, 2], c[:, 1] + c[:, 3])
+        d1, d2 = c[:, 2] - c[:, 0], c[:, 3] - c[:, 1]
+        area = 0.5 * np.abs(d1[:, 0] * d2[:, 1] - d1[:, 1] * d2[:, 0])
+        assert np.isclose(area.sum(), 1.0 * 0.1)       # seam cell included: total = Lx * Ly
+        if ho:                                         # edge nodes 4 .. 4+p-2 lie on the edge between corners 0 and 1
+            e = pts[conn[:, 4:4 + p - 1], :2]
+            for k in range(p - 1):
+                a0, a1 = e[:, k] - c[:, 0], c[:, 1] - c[:, 0]
+                assert np.allclose(a0[:, 0] * a1[:, 1] - a0[:, 1] * a1[:, 0], 0.0, atol=1e-14)
+                assert np.all((a0 * a1).sum(axis=1) > 0) and np.all((a0 * a1).sum(axis=1) < (a1 * a1).sum(axis=1))
+        pd = {d.get("Name"): np.array(d.text.split(), dtype=float) for d in piece.findall("PointData/DataArray")}
+        # periodic field sampled at the cell's own coordinates
+        assert np.allclose(pd["eta"], np.cos(2 * np.pi * pts[:, 0])) and np.allclose(pd["phi_fs"], 2 * pd["eta"])

@@ -15,3 +15,32 @@ def test_series_matches_wronskian_closed_form_on_the_cylinder():
                        mf.envelope(k, a, np.full(5, a), -np.array([0.3, 1.0, 2.0, 2.5, 3.0])), atol=1e-12)
     far = mf.envelope(k, 1e-3, np.array([5.0, 7.0]), np.array([0.4, 2.0]))
     assert np.abs(far - 1.0).max() < 1e-4
+
+
+def test_library_series_matches_scipy_restatement(lpf):
+    """lpf_maccamy_fuchs (std::cyl_bessel_j / cyl_neumann, product) vs the scipy restatement (oracle)."""
+    import maccamy_fuchs as mf
+    k, a = 2.0 * np.pi, 0.5
+    phi = np.linspace(0.0, np.pi, 37)
+    for r in (a, 0.75, 2.0):
+        e_lib = lpf.maccamy_fuchs(k, a, np.full_like(phi, r), phi)
+        e_ref = mf.envelope(k, a, np.full_like(phi, r), phi)
+        assert np.abs(e_lib - e_ref).max() < 1e-9
+    # other ka
+    for ka in (0.3, 1.0, 6.0):
+        e_lib = lpf.maccamy_fuchs(ka / a, a, np.full_like(phi, a), phi)
+        assert np.abs(e_lib - mf.envelope_on_cylinder_wronskian(ka / a, a, phi, nterms=80)).max() < 1e-8
+
+
+def test_reference_stopping_rule_quirk_at_right_angles(lpf):
+    """cylinder-exact.cpp's rule |Re(term)| < tol twice in a row fires at m = 1 for phi = pi/2; everywhere else the
+    reference's values and the library's agree to the series tolerance."""
+    import maccamy_fuchs as mf
+    k, a = 2.0 * np.pi, 0.5
+    phi = np.array([0.0, 0.4, 1.0, 2.0, 2.7, np.pi])
+    ref = mf.envelope_reference_rule(k, a, np.full_like(phi, a), phi)
+    assert np.abs(lpf.maccamy_fuchs(k, a, np.full_like(phi, a), phi) - ref).max() < 1e-8
+    bad = mf.envelope_reference_rule(k, a, np.array([a]), np.array([np.pi / 2]))[0]
+    good = lpf.maccamy_fuchs(k, a, np.array([a]), np.array([np.pi / 2]))[0]
+    assert abs(good - mf.envelope_on_cylinder_wronskian(k, a, np.array([np.pi / 2]))[0]) < 1e-9
+    assert abs(bad - good) > 1e-2

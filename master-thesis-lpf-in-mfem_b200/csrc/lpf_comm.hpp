@@ -12,6 +12,7 @@ namespace lpf {
 struct HaloPlan {
     int n_nbr = 0, total = 0, n_shared = 0;
     std::vector<int> nbr_rank, nbr_offset;      // host copies drive the send/recv group
+    std::vector<int> h_send, h_shared;          // host copies of send_dofs / shared (LL send lists are built from them)
     int *send_dofs = nullptr, *shared = nullptr, *red_off = nullptr, *red_src = nullptr;   // device
     double *sendbuf = nullptr, *recvbuf = nullptr;                                          // device
 };

@@ -122,11 +122,12 @@ struct lpf_ctx {
     std::vector<char> peer_opened;
     P2PPlanDev p2p_plan[2]{};
     int *p2p_send_nbr[2] = {nullptr, nullptr};
-    double **p2p_dst[2] = {nullptr, nullptr};
     P2PDev p2p{};
     P2PTail tail{};           // set around PCG applies when the exchange rides on the apply kernel
     unsigned int *p2p_done = nullptr;
-    int p2p_fuse = 1;         // option: fuse halo-sum / all-reduces into the apply / update kernels
+    int p2p_fuse = 0;         // option: run the halo-sum + (d, A d) all-reduce in the LAST CTA of the apply kernel instead of
+                              // the separate multi-CTA LL kernel (measured slower: 32 vs 21 us per iteration at 2 x 150k dofs)
+    int p2p_fuse_max = 2048;  // ... while the interface has at most this many entries (one CTA runs the tail)
     // host staging for *_host entry points
     double *hx = nullptr, *hy = nullptr;
     // CUDA graph of one PCG chunk
@@ -298,13 +299,14 @@ int halo_sum(lpf_ctx *c, lpf::HaloPlan &h, double *v)
 {
     if (c->nranks == 1 || h.n_nbr == 0) return LPF_OK;
     if (c->p2p_on) {
+        // one multi-CTA kernel: LL lines into the neighbours' boxes, poll, rank-ordered sum (p2p.cuh)
         const int plan = (&h == &c->halo) ? 0 : 1;
         const P2PPlanDev &pd = c->p2p_plan[plan];
-        const int gp = std::max(1, std::min((h.total + 255) / 256, 64)), gu = std::max(1, std::min((h.n_shared + 255) / 256, 64));
-        p2p_pack_kernel<<<gp, 256, 0, c->stream>>>(c->p2p, pd, plan, v);
-        p2p_unpack_kernel<<<gu, 256, 0, c->stream>>>(c->p2p, pd, plan, v);
-        c->launches += 2;
-        CUDA_TRY(cudaGetLastError());
+        const int g = std::max(1, std::min((h.n_shared + 127) / 128, 2 * c->sm_count));
+        PcgState *no_state = nullptr;
+        double *no_slots = nullptr;
+        CUDA_TRY(launch_ex(false, p2p_halo_ll_kernel, dim3(g), dim3(128), 0, c->stream, c->p2p, pd, plan, v, no_state, no_slots, 0));
+        c->launches++;
         return LPF_OK;
     }
     if (!c->comm.ready()) { lpf::set_error("multi-rank context used before lpf_comm_init / lpf_p2p_connect"); return LPF_ERR_STATE; }
@@ -327,6 +329,8 @@ int upload_halo(lpf::HaloPlan &h, int n_nbr, const int *nbr_rank, const int *nbr
     h.total = n_nbr ? nbr_offset[n_nbr] : 0;
     h.n_shared = n_shared;
     if (h.total == 0) return LPF_OK;
+    h.h_send.assign(send, send + h.total);
+    h.h_shared.assign(shared, shared + n_shared);
     LPF_TRY(upload(h.send_dofs, send, (size_t)h.total, bytes));
     LPF_TRY(upload(h.shared, shared, (size_t)n_shared, bytes));
     LPF_TRY(upload(h.red_off, red_off, (size_t)n_shared + 1, bytes));
@@ -341,15 +345,16 @@ int p2p_create(lpf_ctx *c)
 {
     const size_t hdr = (sizeof(P2PBox) + 255) & ~(size_t)255;
     const size_t n0 = (size_t)c->halo.total, n1 = (size_t)c->shalo.total;
-    c->box_bytes = hdr + 2 * (n0 + n1) * sizeof(double) + 256;
+    const size_t ll0 = hdr;                                                               // LL areas: 16-byte lines
+    c->box_bytes = ll0 + 2 * (n0 + n1) * sizeof(uint4) + 256;
     CUDA_TRY(cudaMalloc((void **)&c->box, c->box_bytes));
     CUDA_TRY(cudaMemset(c->box, 0, c->box_bytes));
     P2PBox h;
     std::memset(&h, 0, sizeof(h));
-    h.recv_byte_off[0][0] = (long long)hdr;
-    h.recv_byte_off[0][1] = (long long)(hdr + n0 * 8);
-    h.recv_byte_off[1][0] = (long long)(hdr + 2 * n0 * 8);
-    h.recv_byte_off[1][1] = (long long)(hdr + 2 * n0 * 8 + n1 * 8);
+    h.ll_byte_off[0][0] = (long long)ll0;
+    h.ll_byte_off[0][1] = (long long)(ll0 + n0 * 16);
+    h.ll_byte_off[1][0] = (long long)(ll0 + 2 * n0 * 16);
+    h.ll_byte_off[1][1] = (long long)(ll0 + 2 * n0 * 16 + n1 * 16);
     for (int k = 0; k < c->halo.n_nbr; k++) h.off_for_src[0][c->halo.nbr_rank[k]] = c->halo.nbr_offset[k];
     for (int k = 0; k < c->shalo.n_nbr; k++) h.off_for_src[1][c->shalo.nbr_rank[k]] = c->shalo.nbr_offset[k];
     CUDA_TRY(cudaMemcpy(c->box, &h, sizeof(h), cudaMemcpyHostToDevice));
@@ -396,25 +401,51 @@ int p2p_connect_impl(lpf_ctx *c, const void *handles, const uint64_t *raws, cons
         if (h.n_nbr == 0) continue;
         std::vector<int> send_nbr(h.total);
         for (int k = 0; k < h.n_nbr; k++) for (int i = h.nbr_offset[k]; i < h.nbr_offset[k + 1]; i++) send_nbr[i] = k;
-        std::vector<double *> dst(2 * (size_t)h.n_nbr);
+        std::vector<uint4 *> ll_dst(2 * (size_t)h.n_nbr);
         for (int k = 0; k < h.n_nbr; k++) {
             const int s = h.nbr_rank[k];
             P2PBox ph;      // the neighbour's header tells where this rank writes inside its receive area
             CUDA_TRY(cudaMemcpy(&ph, c->peers[s], sizeof(ph), cudaMemcpyDefault));
-            for (int par = 0; par < 2; par++)
-                dst[(size_t)par * h.n_nbr + k] = (double *)((char *)c->peers[s] + ph.recv_byte_off[pl][par]) + ph.off_for_src[pl][c->rank];
+            for (int par = 0; par < 2; par++) {
+                ll_dst[(size_t)par * h.n_nbr + k] = (uint4 *)((char *)c->peers[s] + ph.ll_byte_off[pl][par]) + ph.off_for_src[pl][c->rank];
+            }
         }
+        // LL send lists: for shared dof i the (neighbour, position in that neighbour's block) pairs it goes to
+        std::vector<int> snd_off(h.n_shared + 1, 0), snd_nbr(h.total), snd_pos(h.total);
+        {
+            std::vector<int> where((size_t)std::max(1, std::max(c->ndof, c->nsurf)), -1);
+            for (int i = 0; i < h.n_shared; i++) where[h.h_shared[i]] = i;
+            for (int i = 0; i < h.total; i++) {
+                const int w = where[h.h_send[i]];
+                if (w < 0) { lpf::set_error("lpf_p2p_connect: a sent dof is missing from the shared list"); return LPF_ERR_ARG; }
+                snd_off[w + 1]++;
+            }
+            for (int i = 0; i < h.n_shared; i++) snd_off[i + 1] += snd_off[i];
+            std::vector<int> pos(snd_off.begin(), snd_off.end() - 1);
+            for (int i = 0; i < h.total; i++) {
+                const int w = where[h.h_send[i]], k = send_nbr[i];
+                snd_nbr[pos[w]] = k; snd_pos[pos[w]] = i - h.nbr_offset[k]; pos[w]++;
+            }
+        }
+        int *so = nullptr, *sn = nullptr, *spz = nullptr;
+        uint4 **lld = nullptr;
+        LPF_TRY(upload(so, snd_off.data(), snd_off.size(), &c->bytes));
+        LPF_TRY(upload(sn, snd_nbr.data(), snd_nbr.size(), &c->bytes));
+        LPF_TRY(upload(spz, snd_pos.data(), snd_pos.size(), &c->bytes));
+        LPF_TRY(upload(lld, ll_dst.data(), ll_dst.size(), &c->bytes));
+        pd.snd_off = so; pd.snd_nbr = sn; pd.snd_pos = spz; pd.ll_dst = lld;
         int *nr = nullptr, *no = nullptr;
         LPF_TRY(upload(c->p2p_send_nbr[pl], send_nbr.data(), send_nbr.size(), &c->bytes));
-        LPF_TRY(upload(c->p2p_dst[pl], dst.data(), dst.size(), &c->bytes));
         LPF_TRY(upload(nr, h.nbr_rank.data(), h.nbr_rank.size(), &c->bytes));
         LPF_TRY(upload(no, h.nbr_offset.data(), h.nbr_offset.size(), &c->bytes));
         pd.nbr_rank = nr; pd.nbr_offset = no;          // small tables, freed with the context's device at exit
-        pd.send_dofs = h.send_dofs; pd.send_nbr = c->p2p_send_nbr[pl]; pd.dst = c->p2p_dst[pl];
+        pd.send_dofs = h.send_dofs; pd.send_nbr = c->p2p_send_nbr[pl];
         pd.shared = h.shared; pd.red_off = h.red_off; pd.red_src = h.red_src;
         P2PBox mine;
         CUDA_TRY(cudaMemcpy(&mine, c->box, sizeof(mine), cudaMemcpyDeviceToHost));
-        for (int par = 0; par < 2; par++) pd.recv[par] = (const double *)((char *)c->box + mine.recv_byte_off[pl][par]);
+        for (int par = 0; par < 2; par++) {
+            pd.ll_recv[par] = (const uint4 *)((char *)c->box + mine.ll_byte_off[pl][par]);
+        }
     }
     c->p2p.nranks = R; c->p2p.rank = c->rank; c->p2p.peers = c->peers_dev; c->p2p.mine = c->box; c->p2p.local = c->p2p_local;
     c->p2p_on = true;
@@ -434,6 +465,8 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     if (const char *e = std::getenv("LPF_PDL")) c->pdl = std::atoi(e);          // A/B switches for the drivers
     if (const char *e = std::getenv("LPF_PCG_CHUNK")) c->chunk = std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("LPF_P2P_FUSE")) c->p2p_fuse = std::atoi(e);
+    if (const char *e = std::getenv("LPF_P2P_FUSE_MAX")) c->p2p_fuse_max = std::atoi(e);
     c->p = d->order; c->D = d->order + 1; c->Q = d->order + 2;
     c->ne = d->ne; c->ndof = d->ndof; c->ness = d->n_ess; c->nsurf = d->n_surf;
     c->nranks = d->nranks > 0 ? d->nranks : 1; c->rank = d->rank;
@@ -612,7 +645,7 @@ void lpf_destroy(lpf_ctx *c)
     for (void *p : ptrs) if (p) cudaFree(p);
     free_halo(c->halo); free_halo(c->shalo);
     for (size_t r = 0; r < c->peers.size(); r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
-    void *pp[] = {c->box, c->p2p_local, c->p2p_done, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1], c->p2p_dst[0], c->p2p_dst[1]};
+    void *pp[] = {c->box, c->p2p_local, c->p2p_done, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1]};
     for (void *p : pp) if (p) cudaFree(p);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->state_pinned) cudaFreeHost(c->state_pinned);
@@ -646,6 +679,7 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "skip_zero_apply") c->skip_zero_apply = (int)value;
     else if (k == "p2p_fuse") c->p2p_fuse = (int)value;
     else if (k == "pdl") c->pdl = (int)value;
+    else if (k == "p2p_fuse_max") c->p2p_fuse_max = (int)value;
     else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
     if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
@@ -844,7 +878,7 @@ bool p2p_fused(const lpf_ctx *c)
     const bool tail_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
     // the tail runs in ONE CTA: worth it only while the interface is small (measured: 2 x 585 dofs at big8 p=4 breaks even
     // with NCCL, 2 x 8481 dofs is 2x slower than separate multi-CTA pack / unpack kernels)
-    return c->p2p_on && c->p2p_fuse && !c->ess_general && tail_kernel && c->halo.n_nbr > 0 && c->halo.n_nbr <= 32 && c->halo.total <= 2048;
+    return c->p2p_on && c->p2p_fuse && !c->ess_general && tail_kernel && c->halo.n_nbr > 0 && c->halo.n_nbr <= 32 && c->halo.total <= c->p2p_fuse_max;
 }
 
 // constrained apply whose last CTA also does the halo-sum and the all-reduce of (d, A d)
@@ -857,16 +891,26 @@ int apply_with_tail(lpf_ctx *c, const double *x, double *y)
     return rc;
 }
 
+// LL halo-sum of the PCG apply (+ the (d, A d) all-reduce) in one PDL-chained kernel
+int halo_ll(lpf_ctx *c, bool pdl, double *v, bool with_den)
+{
+    const P2PPlanDev &pd = c->p2p_plan[0];
+    const int g = std::max(1, std::min((c->halo.n_shared + 127) / 128, 2 * c->sm_count));
+    CUDA_TRY(launch_ex(pdl, p2p_halo_ll_kernel, dim3(g), dim3(128), 0, c->stream, c->p2p, pd, 0, v, c->st, c->den_slots, (int)with_den));
+    c->launches++;
+    return LPF_OK;
+}
+
 int pcg_iteration(lpf_ctx *c)
 {
     const int n = c->ndof, g = vec_grid(n, c->sm_count);
     const bool multi = c->nranks > 1;
     const uint8_t *no_mask = nullptr;
     const bool tma_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
+    const bool pdl = c->pdl != 0 && tma_kernel && !c->ess_general;
     if (p2p_fused(c)) {
         // three launches, as on one GPU: the betanom all-reduce runs in the last block of the update kernel, the
         // halo-sum and the (d, A d) all-reduce in the last CTA of the apply kernel (peer-memory stores + flags)
-        const bool pdl = c->pdl != 0;
         CUDA_TRY(launch_ex(pdl, pcg_update_p2p_kernel, dim3(g), dim3(256), 0, c->stream, n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->partials, c->p2p));
         CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
         c->launches += 2;
@@ -874,6 +918,18 @@ int pcg_iteration(lpf_ctx *c)
         const int rc = apply_with_tail(c, c->d, c->ad);
         c->pdl_now = false;
         return rc;
+    }
+    if (multi && c->p2p_on && !c->ess_general) {
+        // four PDL-chained launches: update (+ betanom all-reduce in its last block), direction, apply, LL halo-sum
+        // (+ (d, A d) all-reduce).  Two NVLink one-way latencies per iteration, no NCCL, no host involvement.
+        CUDA_TRY(launch_ex(pdl, pcg_update_p2p_kernel, dim3(g), dim3(256), 0, c->stream, n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->partials, c->p2p));
+        CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
+        c->launches += 2;
+        c->pdl_now = pdl;
+        const int rc = apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status);
+        c->pdl_now = false;
+        LPF_TRY(rc);
+        return halo_ll(c, pdl, c->ad, true);
     }
     if (multi) {
         pcg_update_kernel<true><<<g, 256, 0, c->stream>>>(n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->den_slots, c->partials);
@@ -885,7 +941,6 @@ int pcg_iteration(lpf_ctx *c)
     } else {
         // single GPU: update -> direction -> apply chained by programmatic dependent launches (the ess_fix kernel of
         // general right-hand sides has no griddep_wait, so that path keeps plain stream order)
-        const bool pdl = c->pdl != 0 && tma_kernel && !c->ess_general;
         CUDA_TRY(launch_ex(pdl, pcg_update_kernel<false>, dim3(g), dim3(256), 0, c->stream, n, c->X, c->r, c->z, c->d, c->ad, c->dinv, no_mask, c->st, c->den_slots, c->partials));
         CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
         c->launches += 2;
@@ -953,10 +1008,16 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         c->launches++;
         t = c->tmp;
     }
+    const bool ll_path = multi && c->p2p_on && !c->ess_general && !p2p_fused(c);
     if (p2p_fused(c)) {
         pcg_init_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials, c->p2p);
         c->launches++;
         LPF_TRY(apply_with_tail(c, c->d, c->ad));
+    } else if (ll_path) {
+        pcg_init_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials, c->p2p);
+        c->launches++;
+        LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+        LPF_TRY(halo_ll(c, false, c->ad, true));
     } else if (multi) {
         pcg_init_kernel<true><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
@@ -965,7 +1026,7 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         pcg_init_kernel<false><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, nullptr, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
     }
-    if (!p2p_fused(c)) {
+    if (!p2p_fused(c) && !ll_path) {
         LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
         LPF_TRY(ess_fix(c));
         if (multi) {

@@ -4,6 +4,9 @@
 // (PF_linear_par_partial.cpp:255-261, 298-306, 359-360, 415-447); every one can be overridden:
 //   --mesh wave-tank-finite.mesh|<file>  --order 4  --ref 0  --nsteps 180  --periods 5  --gpus 1
 //   --no-relax   --cylinder (mesh tests/meshes/cylinder_half.mesh, third absorption weight, eta envelope)
+//   --serial-params: the constants of Solvers/PF_linear_serial.cpp (BASELINE config 2: order 5, 1 refinement, H = 0.05,
+//                    wave chosen by its period T = 1.13392/3, Ng = Ns = 2, 800 steps over 8 T, PCG rel 1e-12 / 400 it) --
+//                    with the PA + Jacobi-PCG solver of this library in place of the assembled matrix + GS-PCG
 #include <algorithm>
 #include <chrono>
 #include <mutex>
@@ -17,8 +20,9 @@ int main(int argc, char *argv[])
     Args a{argc, argv};
     try {
         const bool cyl = a.has("--cylinder");
-        const int order = a.geti("--order", 4);
-        const int ref_levels = a.geti("--ref", 0);
+        const bool serial = a.has("--serial-params");
+        const int order = a.geti("--order", serial ? 5 : 4);                    // PF_linear_serial.cpp:266-267
+        const int ref_levels = a.geti("--ref", serial ? 1 : 0);
         const int num_procs = a.geti("--gpus", 1);
         const bool relax = !a.has("--no-relax");
         const std::string mesh_file = a.get("--mesh", cyl ? "../../../tests/meshes/cylinder_half.mesh" : "wave-tank-finite.mesh");
@@ -28,8 +32,9 @@ int main(int argc, char *argv[])
         Wave w;                                   // H = 0.01, g = 9.81, lambda = 1, kh = 1  (:287-306)
         double lo[3], hi[3];
         mesh->GetBoundingBox(lo, hi);
-        const int nsteps = a.geti("--nsteps", cyl ? 350 : 180);              // :359 / cylinder-diffraction.cpp:252
-        const double t_final = a.getd("--periods", cyl ? 10.0 : 5.0) * w.T;
+        if (serial) { w.H = 0.05; w.period_mode(1.13392 / 3, hi[2] - lo[2], 40); }   // PF_linear_serial.cpp:307-327
+        const int nsteps = a.geti("--nsteps", serial ? 800 : cyl ? 350 : 180);        // :359 / cylinder-diffraction.cpp:252 / serial :341-344
+        const double t_final = a.getd("--periods", serial ? 8.0 : cyl ? 10.0 : 5.0) * w.T;
         const double dt = t_final / nsteps;
         const double t_last_start = t_final - w.T;
         printf("Wave parameters:\n  Lx     = %g\n  lwave  = %g\n  kh     = %g\n  k      = %g\n  cwave  = %g\n  T      = %g\n  omega  = %g\n  H      = %g\n",
@@ -51,7 +56,7 @@ int main(int argc, char *argv[])
                 state[ns + s] = w.phi_fs(0.0, x, y);
                 // relaxation functions Cgen / Cabs (:415-447); cylinder: Ng 2.5, Ns 4, plus Cabsy over the last
                 // 3 lambda in y (cylinder-diffraction.cpp:373-389) -- absorption weights add up in the RHS
-                const double Ng = 2.5, Ns = 4.0, xg0 = lo[0], xg1 = xg0 + Ng * w.lambda, x1 = hi[0], x0 = x1 - Ns * w.lambda;
+                const double Ng = serial ? 2.0 : 2.5, Ns = serial ? 2.0 : 4.0, xg0 = lo[0], xg1 = xg0 + Ng * w.lambda, x1 = hi[0], x0 = x1 - Ns * w.lambda;
                 double cg;
                 if (x <= xg0) cg = 1.0; else if (x >= xg1) cg = 0.0;
                 else { const double xi = (x - xg0) / (xg1 - xg0); cg = 1 - (-2.0 * xi * xi * xi + 3.0 * xi * xi); }
@@ -64,7 +69,7 @@ int main(int argc, char *argv[])
                 cgen[s] = cg; cabs[s] = ca;
             }
             RhsLinear surface(fespace, myid, world);
-            surface.Setup(w.params(dt, relax, 1e-12, cyl ? 2000 : 1000), cgen.data(), cabs.data());   // :157-164, tau = dt :470
+            surface.Setup(w.params(dt, relax, 1e-12, serial ? 400 : cyl ? 2000 : 1000), cgen.data(), cabs.data());   // :157-164, tau = dt :470
             surface.SetState(state);
             std::vector<double> env(ns, -1e300);
             // ParaView output of eta / phi_fs every 5 steps (:453-467, 505-514); off unless --paraview <name> is given

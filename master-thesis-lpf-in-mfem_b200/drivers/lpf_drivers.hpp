@@ -115,6 +115,19 @@ struct Wave {
         omega = 2.0 * M_PI / T;
         kx_dir = std::cos(theta); ky_dir = std::sin(theta);
     }
+    /// "period mode" of Solvers/PF_linear_serial.cpp:22-34,320-327: the wave is chosen by its period; kh from the
+    /// fixed-point iteration kh <- sqrt(w^2 h / g * kh * coth(kh)), n_iter times
+    void period_mode(double T_input, double h, int n_iter = 40)
+    {
+        const double wq = 2.0 * M_PI / T_input;
+        double x = std::max(wq * wq * h / g, 1e-8);
+        for (int i = 0; i < n_iter; i++) {
+            const double xs = std::max(x, 1e-12);
+            x = std::max(std::sqrt((wq * wq / g) * h * x * (std::cosh(xs) / std::sinh(xs))), 1e-8);
+        }
+        kh = x; T = T_input; omega = wq; k = kh / h; cwave = omega / k; lambda = 2.0 * M_PI / k;
+        kx_dir = std::cos(theta); ky_dir = std::sin(theta);
+    }
     double phase(double t, double x, double y) const { return omega * t - k * (kx_dir * x + ky_dir * y); }
     double eta(double t, double x, double y) const { return 0.5 * H * std::cos(phase(t, x, y)); }
     double phi_fs(double t, double x, double y) const { return -0.5 * H * cwave * std::cosh(kh) / std::sinh(kh) * std::sin(phase(t, x, y)); }

@@ -715,6 +715,16 @@ Partition::Partition(const Mesh &mesh, const H1Space &space, int nranks_, int ra
         }
         corners.insert(corners.end(), mesh.corners.begin() + (size_t)e * 24, mesh.corners.begin() + (size_t)(e + 1) * 24);
     }
+    if (nranks > 1) {
+        // Local dofs in ascending GLOBAL id: the entity-based global numbering keeps the dofs of an edge / face / interior
+        // contiguous (16.5 cache lines per order-4 element instead of 21.5 with first-touch numbering, which cost 5 % of
+        // the apply kernel on partitioned meshes).
+        std::vector<int> remap(l2g.size());
+        std::sort(l2g.begin(), l2g.end());
+        std::vector<int> old = g2l;
+        for (size_t l = 0; l < l2g.size(); l++) { remap[old[l2g[l]]] = (int)l; g2l[l2g[l]] = (int)l; }
+        for (int &g : gather) g = remap[g];
+    }
     const int nl = (int)l2g.size();
     std::vector<uint64_t> mask(nl, 0);
     std::vector<int> gsurf(space.ndof, -1);

@@ -243,6 +243,9 @@ int lpf_time_apply(lpf_ctx *ctx, const double *x_dev, double *y_dev, int reps, f
 long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launched by this context so far */
 int lpf_set_option(lpf_ctx *ctx, const char *name, long value);   /* kernel variant knobs, see DESIGN.md */
 size_t lpf_device_bytes(const lpf_ctx *ctx);
+/* 1 if the affine fast path (element tensor instead of stored q-data; option "affine", on by default) is in use:
+ * decided by lpf_pa_setup -- every element of the rank must be an affine hex */
+int lpf_affine_active(const lpf_ctx *ctx);
 
 /* plain device memory helpers so hosts without a CUDA runtime binding can drive the library */
 void *lpf_dev_alloc(size_t bytes);

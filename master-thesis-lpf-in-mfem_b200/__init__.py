@@ -132,6 +132,7 @@ SIGNATURES = {
     "lpf_launch_count": (C.c_long, [_VP]),
     "lpf_set_option": (C.c_int, [_VP, C.c_char_p, C.c_long]),
     "lpf_device_bytes": (C.c_size_t, [_VP]),
+    "lpf_affine_active": (C.c_int, [_VP]),
     "lpf_dev_alloc": (_VP, [C.c_size_t]),
     "lpf_dev_free": (C.c_int, [_VP]),
     "lpf_memcpy_h2d": (C.c_int, [_VP, _VP, C.c_size_t]),
@@ -490,6 +491,10 @@ class Context:
     @property
     def launches(self):
         return lib.lpf_launch_count(self.h)
+
+    @property
+    def affine_active(self):
+        return bool(lib.lpf_affine_active(self.h))
 
     @property
     def device_bytes(self):

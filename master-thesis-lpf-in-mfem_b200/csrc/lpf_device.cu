@@ -90,6 +90,9 @@ struct lpf_ctx {
     int ess_general = 0;      // lpf_pcg: search directions may be non-zero on essential dofs
     // geometry / maps
     double *corners = nullptr, *jac = nullptr, *jinv_z = nullptr, *qd = nullptr;
+    double *qa = nullptr;     // affine fast path: [ne][6] element tensors
+    int affine = 1;           // option: use the fast path when every element is affine
+    bool affine_ok = false;   // decided by lpf_pa_setup
     int *gmap = nullptr, *gmap_c = nullptr, *ess = nullptr;
     uint8_t *essmask = nullptr, *owned = nullptr, *surf_owned = nullptr;
     // solver vectors
@@ -184,13 +187,13 @@ int apply_pipe_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y,
     return LPF_OK;
 }
 
-template <int P, int E, int MINB, bool EO = false>
+template <int P, int E, int MINB, bool EO = false, bool AFF = false>
 int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
 {
-    using C = TmaCfg<P, E>;
+    using C = TmaCfg<P, E, AFF>;
     static int blocks_per_sm[16] = {0};
-    auto kd = EO ? pa_apply_eo_kernel<P, E, true, MINB> : pa_apply_tma_kernel<P, E, true, MINB>;
-    auto kn = EO ? pa_apply_eo_kernel<P, E, false, MINB> : pa_apply_tma_kernel<P, E, false, MINB>;
+    auto kd = EO ? pa_apply_eo_kernel<P, E, true, MINB, AFF> : pa_apply_tma_kernel<P, E, true, MINB>;
+    auto kn = EO ? pa_apply_eo_kernel<P, E, false, MINB, AFF> : pa_apply_tma_kernel<P, E, false, MINB>;
     int &bps = blocks_per_sm[c->dev & 15];
     if (bps == 0) {
         CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
@@ -201,7 +204,7 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
     const int nb = (c->ne + E - 1) / E;
     if (nb == 0) return LPF_OK;
     const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
-    CUDA_TRY(launch_ex(c->pdl_now, den ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c->stream, c->qd, gmap, x, y, c->ne, den, status, c->tail));
+    CUDA_TRY(launch_ex(c->pdl_now, den ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c->stream, AFF ? c->qa : c->qd, gmap, x, y, c->ne, den, status, c->tail));
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
@@ -214,6 +217,7 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
 // E-vector applies (AddMultPA adapter entry point) use the one-batch-per-CTA kernel.
 #define LPF_TMA(P, E, MINB) return apply_tma_launch_t<P, E, MINB>(c, gmap, x, y, den, status)
 #define LPF_EO(P, E, MINB) return apply_tma_launch_t<P, E, MINB, true>(c, gmap, x, y, den, status)
+#define LPF_EOA(P, E, MINB) return apply_tma_launch_t<P, E, MINB, true, true>(c, gmap, x, y, den, status)
 #define LPF_OLD(P, E, PF) return apply_launch_t<P, E, PF, EVEC, 1>(c, gmap, x, y, den, status)
 template <bool EVEC>
 int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
@@ -240,6 +244,19 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
         }
     }
     if constexpr (!EVEC) {
+        if (v == 0 && c->affine && c->affine_ok) {      // affine fast path: no q-data stream (pa_apply_eo.cuh)
+            switch (c->p) {
+                case 1: LPF_EOA(1, 16, 4);
+                case 2: LPF_EOA(2, 8, 4);
+                case 3: LPF_EOA(3, 8, 2);
+                case 4: LPF_EOA(4, 3, 4);
+                case 5: LPF_EOA(5, 3, 2);
+                case 6: LPF_EOA(6, 2, 3);
+                case 7: LPF_EOA(7, 1, 2);
+                case 8: LPF_EOA(8, 1, 2);
+                default: break;
+            }
+        }
         if (v == 0) {                 // tuned defaults (profiles/r01_sweep_orders.txt): even-odd kernel from order 3 up
             switch (c->p) {
                 case 3: LPF_EO(3, 8, 2);
@@ -292,6 +309,7 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
 }
 #undef LPF_TMA
 #undef LPF_EO
+#undef LPF_EOA
 #undef LPF_OLD
 
 
@@ -466,6 +484,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     if (const char *e = std::getenv("LPF_PDL")) c->pdl = std::atoi(e);          // A/B switches for the drivers
     if (const char *e = std::getenv("LPF_PCG_CHUNK")) c->chunk = std::max(1, std::atoi(e));
     if (const char *e = std::getenv("LPF_P2P_FUSE")) c->p2p_fuse = std::atoi(e);
+    if (const char *e = std::getenv("LPF_AFFINE")) c->affine = std::atoi(e);
     if (const char *e = std::getenv("LPF_P2P_FUSE_MAX")) c->p2p_fuse_max = std::atoi(e);
     c->p = d->order; c->D = d->order + 1; c->Q = d->order + 2;
     c->ne = d->ne; c->ndof = d->ndof; c->ness = d->n_ess; c->nsurf = d->n_surf;
@@ -542,6 +561,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         LPF_TRY(upload(c->ess, d->ess, (size_t)c->ness, &c->bytes));
     }
     LPF_TRY(upload(c->qd, (const double *)nullptr, (size_t)c->ne * 6 * Q3, &c->bytes));
+    if (d->corners) LPF_TRY(upload(c->qa, (const double *)nullptr, (size_t)c->ne * 6, &c->bytes));
     const size_t n = (size_t)c->ndof;
     LPF_TRY(upload(c->dinv, (const double *)nullptr, n, &c->bytes));
     LPF_TRY(upload(c->r, (const double *)nullptr, n, &c->bytes));
@@ -638,7 +658,7 @@ void lpf_destroy(lpf_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->pcg_graph) cudaGraphExecDestroy(c->pcg_graph);
     c->comm.destroy();
-    void *ptrs[] = {c->corners, c->jac, c->jinv_z, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
+    void *ptrs[] = {c->qa, c->corners, c->jac, c->jinv_z, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
                     c->z, c->d, c->ad, c->X, c->Bv, c->tmp, c->den_slots, c->partials, c->st, c->bad, c->surf2vol,
                     c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->cabsy, c->env, c->wsum, c->rk_k,
                     c->rk_y, c->rk_z, c->state_dev};
@@ -668,6 +688,7 @@ int lpf_ndof(const lpf_ctx *c) { return c ? c->ndof : LPF_ERR_ARG; }
 int lpf_nsurf(const lpf_ctx *c) { return c ? c->nsurf : LPF_ERR_ARG; }
 long lpf_launch_count(lpf_ctx *c) { return c ? c->launches : 0; }
 size_t lpf_device_bytes(const lpf_ctx *c) { return c ? c->bytes : 0; }
+int lpf_affine_active(const lpf_ctx *c) { return c ? (int)(c->affine && c->affine_ok) : 0; }
 
 int lpf_set_option(lpf_ctx *c, const char *name, long value)
 {
@@ -679,6 +700,7 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "skip_zero_apply") c->skip_zero_apply = (int)value;
     else if (k == "p2p_fuse") c->p2p_fuse = (int)value;
     else if (k == "pdl") c->pdl = (int)value;
+    else if (k == "affine") c->affine = (int)value;
     else if (k == "p2p_fuse_max") c->p2p_fuse_max = (int)value;
     else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
@@ -734,6 +756,16 @@ int lpf_pa_setup(lpf_ctx *c)
         pa_setup_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c->stream>>>(c->p, c->ne, c->corners, c->jac, c->qd);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
+    }
+    c->affine_ok = false;
+    if (c->ne && c->corners && !c->jac && c->qa) {      // affine fast path: element tensors + "is every element affine?"
+        CUDA_TRY(cudaMemsetAsync(c->bad, 0, sizeof(int), c->stream));
+        pa_affine_setup_kernel<<<(c->ne + 127) / 128, 128, 0, c->stream>>>(c->ne, c->corners, c->qa, c->bad);
+        c->launches++;
+        int not_affine = 0;
+        CUDA_TRY(cudaMemcpyAsync(&not_affine, c->bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->affine_ok = !not_affine;
     }
     c->setup_done = true;
     return LPF_OK;

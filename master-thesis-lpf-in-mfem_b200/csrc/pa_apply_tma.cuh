@@ -47,7 +47,7 @@ __device__ __forceinline__ void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int P, int E>
+template <int P, int E, bool AFF = false>      // AFF: affine fast path, no q-data staging area (pa_apply_eo.cuh)
 struct TmaCfg : ApplyCfg<P, E> {
     using B = ApplyCfg<P, E>;
     static constexpr int D3 = B::D * B::D * B::D;
@@ -55,7 +55,7 @@ struct TmaCfg : ApplyCfg<P, E> {
     static constexpr int QE = 6 * B::Q * B::Q * B::Q;               // doubles of q-data per element
     // byte offsets inside dynamic shared memory
     static constexpr size_t OFF_Q = 0;                                                  // [E][QE] doubles (16B aligned)
-    static constexpr size_t OFF_IDX = OFF_Q + (size_t)E * QE * 8;                       // [2][E][DP3] ints
+    static constexpr size_t OFF_IDX = OFF_Q + (AFF ? (size_t)0 : (size_t)E * QE * 8);   // [2][E][DP3] ints
     static constexpr size_t OFF_WORK = (OFF_IDX + (size_t)2 * E * DP3 * 4 + 15) & ~(size_t)15;
     static constexpr size_t OFF_BAR = (OFF_WORK + (size_t)E * B::ES * 8 + 15) & ~(size_t)15;   // 3 mbarriers
     static constexpr size_t SMEM_BYTES = OFF_BAR + 64;

@@ -55,6 +55,37 @@ __host__ __device__ constexpr int lpf_pad_to(int v, int target_mod16)
     return w;
 }
 
+// Affine fast path set-up: one thread per element.  qa[e][6] = (D11, D21, D31, D22, D32, D33) of detJ J^-1 J^-T (no
+// quadrature weight) from the constant Jacobian of an affine hex; *not_affine is raised if any element's trilinear map
+// has a bilinear / trilinear part larger than 1e-13 of its edge length (then the fast path stays off).
+__global__ void pa_affine_setup_kernel(int ne, const double *__restrict__ corners, double *__restrict__ qa, int *not_affine)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const double *C = corners + (size_t)e * 24;
+    double J[3][3], dev = 0.0, len = 0.0;
+    for (int c = 0; c < 3; c++) {
+        const double c0 = C[c], c1 = C[3 + c], c2 = C[6 + c], c3 = C[9 + c], c4 = C[12 + c], c5 = C[15 + c], c6 = C[18 + c], c7 = C[21 + c];
+        J[c][0] = c1 - c0; J[c][1] = c2 - c0; J[c][2] = c4 - c0;
+        dev = fmax(dev, fmax(fmax(fabs(c3 - (c1 + c2 - c0)), fabs(c5 - (c1 + c4 - c0))),
+                             fmax(fabs(c6 - (c2 + c4 - c0)), fabs(c7 - (c1 + c2 + c4 - 2.0 * c0)))));
+        len = fmax(len, fmax(fabs(J[c][0]), fmax(fabs(J[c][1]), fabs(J[c][2]))));
+    }
+    if (dev > 1e-13 * len) atomicOr(not_affine, 1);
+    const double A11 = J[1][1] * J[2][2] - J[1][2] * J[2][1], A12 = J[2][1] * J[0][2] - J[0][1] * J[2][2], A13 = J[0][1] * J[1][2] - J[1][1] * J[0][2];
+    const double A21 = J[2][0] * J[1][2] - J[1][0] * J[2][2], A22 = J[0][0] * J[2][2] - J[0][2] * J[2][0], A23 = J[1][0] * J[0][2] - J[0][0] * J[1][2];
+    const double A31 = J[1][0] * J[2][1] - J[2][0] * J[1][1], A32 = J[2][0] * J[0][1] - J[0][0] * J[2][1], A33 = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double det = J[0][0] * A11 + J[0][1] * A21 + J[0][2] * A31;
+    const double s = 1.0 / det;
+    double *q = qa + (size_t)e * 6;
+    q[0] = s * (A11 * A11 + A12 * A12 + A13 * A13);
+    q[1] = s * (A11 * A21 + A12 * A22 + A13 * A23);
+    q[2] = s * (A11 * A31 + A12 * A32 + A13 * A33);
+    q[3] = s * (A21 * A21 + A22 * A22 + A23 * A23);
+    q[4] = s * (A21 * A31 + A22 * A32 + A23 * A33);
+    q[5] = s * (A31 * A31 + A32 * A32 + A33 * A33);
+}
+
 template <int P, int E>
 struct ApplyCfg {
     static constexpr int D = P + 1, Q = P + 2;

@@ -352,6 +352,47 @@ def test_cylinder_rhs_third_weight_and_envelope(lpf, orc, cuda):
     ctx.close()
 
 
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_affine_fast_path(lpf, orc, cuda, tank, p):
+    """Affine hexes: D(q) = w_q * (detJ J^-1 J^-T) from one 6-entry tensor per element instead of stored q-data.
+    Same operator to 1e-12, same solve; switched off automatically on a non-affine mesh."""
+    torch = cuda
+    m = lpf.Mesh.wave_tank(5, 2, 3).refine(1) if p <= 4 else lpf.Mesh.wave_tank(4, 1, 2)
+    sp = lpf.Space(m, p)
+    osp = oracle_space_from(orc, sp)
+    A = orc.PAOperator(osp)
+    x = orc.hash_noise(sp.ndof)
+    ref = orc.ConstrainedOperator(A, np.sort(sp.ess)).mult(x)
+    xd, yd = _dev(torch, x), torch.empty(sp.ndof, dtype=torch.float64, device="cuda")
+    ctx = _ctx(lpf, torch, sp)
+    assert ctx.affine_active
+    ctx.set_option("max_ctas", 7)                 # several batches per persistent CTA
+    ctx.apply_T(xd, yd)
+    y_aff = yd.cpu().numpy().copy()
+    assert rel_err(y_aff, ref) < TOL_OP
+    ctx.set_option("affine", 0)
+    assert not ctx.affine_active
+    ctx.apply_T(xd, yd)
+    assert rel_err(yd.cpu().numpy(), ref) < TOL_OP and rel_err(yd.cpu().numpy(), y_aff) < TOL_OP
+    # Laplace solve: same potential, iteration counts within +-1 of the stored-q-data path
+    ctx.jacobi_setup()
+    phi0 = np.zeros(sp.ndof)
+    phi0[sp.surf2vol] = np.cos(2 * np.pi * sp.surf_xy[:, 0])
+    pd0 = _dev(torch, phi0)
+    i0 = ctx.laplace_solve(pd0, rel_tol=1e-10, max_iter=2000)
+    ctx.set_option("affine", 1)
+    pd1 = _dev(torch, phi0)
+    i1 = ctx.laplace_solve(pd1, rel_tol=1e-10, max_iter=2000)
+    assert i0.converged and i1.converged and abs(i0.iterations - i1.iterations) <= 1
+    assert rel_err(pd1.cpu().numpy(), pd0.cpu().numpy()) < 1e-8          # both solved to rel 1e-10
+    ctx.close()
+    # a perturbed copy of the same mesh is not affine: the fast path must stay off by itself
+    sp2 = lpf.Space(tank, min(p, 3))
+    c2 = _ctx(lpf, torch, sp2)
+    assert not c2.affine_active
+    c2.close()
+
+
 def test_golden_vectors(lpf, cuda):
     """Committed oracle outputs (tests/golden/tank_p3.npz, made by make_golden.py) through the
     arrays-only descriptor route an MFEM adapter would take."""

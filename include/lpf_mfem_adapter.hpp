@@ -150,13 +150,20 @@ private:
 /// rhs_linear (PF_linear_par_partial.cpp:36-245): state = [eta ; phi_fs] in surface true dofs.
 class B200RhsLinear : public mfem::TimeDependentOperator {
 public:
-    B200RhsLinear(B200Context &c, const lpf_rhs_params &prm, const mfem::Vector *cgen, const mfem::Vector *cabs)
+    /// cabsy: the third weight of Solvers/cylinder-diffraction.cpp:373-389 (Cabsy_gf), NULL for the wave-tank drivers
+    B200RhsLinear(B200Context &c, const lpf_rhs_params &prm, const mfem::Vector *cgen, const mfem::Vector *cabs,
+                  const mfem::Vector *cabsy = nullptr)
         : mfem::TimeDependentOperator(2 * lpf_nsurf(c.get())), c_(c)
     {
         check(lpf_pa_setup(c_.get()), "lpf_pa_setup");
         check(lpf_jacobi_setup(c_.get()), "lpf_jacobi_setup");
         check(lpf_rhs_setup(c_.get(), &prm, cgen ? cgen->HostRead() : nullptr, cabs ? cabs->HostRead() : nullptr), "lpf_rhs_setup");
+        if (cabsy) check(lpf_rhs_set_cabsy(c_.get(), cabsy->HostRead()), "lpf_rhs_set_cabsy");
     }
+    /// eta envelope of cylinder-diffraction.cpp:410-444: call after every Step once t >= t_last_start
+    void EnvelopeReset() { check(lpf_envelope_reset(c_.get()), "lpf_envelope_reset"); }
+    void EnvelopeUpdate(const mfem::Vector &state) { check(lpf_envelope_update(c_.get(), state.Read()), "lpf_envelope_update"); }
+    void EnvelopeGet(mfem::Vector &env, double scale) { check(lpf_envelope_get(c_.get(), env.HostWrite(), scale), "lpf_envelope_get"); }
     void Mult(const mfem::Vector &x, mfem::Vector &dxdt) const override
     {
         check(lpf_rhs(c_.get(), GetTime(), x.Read(), dxdt.Write()), "lpf_rhs");

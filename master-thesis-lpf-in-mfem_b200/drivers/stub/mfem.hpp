@@ -34,6 +34,7 @@ public:
     double *Write() { return data_; }
     double *ReadWrite() { return data_; }
     const double *HostRead() const { return data_; }
+    double *HostWrite() { return data_; }
 private:
     double *data_ = nullptr;
     int size_ = 0;

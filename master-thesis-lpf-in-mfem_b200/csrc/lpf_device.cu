@@ -133,6 +133,16 @@ struct lpf_ctx {
     int p2p_fuse_max = 2048;  // ... while the interface has at most this many entries (one CTA runs the tail)
     // host staging for *_host entry points
     double *hx = nullptr, *hy = nullptr;
+    // pipelined host entry point (lpf_apply_T_host): element chunks / dof ranges, copy streams, events
+    int sub_e0 = 0, sub_ne = -1;               // element sub-range for the next apply launch (-1 = all)
+    int host_pipeline = 1;                     // option
+    std::vector<int> hp_elem_end;              // [K] end element of chunk k
+    std::vector<int> hp_x_ranges_needed;       // [K] number of leading dof ranges chunk k reads
+    std::vector<std::vector<int>> hp_final;    // [K] dof ranges whose y is final once chunk k is done
+    std::vector<int> hp_range_end, hp_ess_end; // [R] end dof of range j, end position in the (sorted) ess list
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> hp_ev_x, hp_ev_c;
+    cudaEvent_t hp_ev_start = nullptr, hp_ev_done = nullptr;
     // CUDA graph of one PCG chunk
     cudaGraphExec_t pcg_graph = nullptr;
     int pcg_graph_chunk = 0, pcg_graph_general = 0, pcg_graph_launches = 0;
@@ -201,10 +211,13 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
         if (bps < 1) bps = 1;
     }
-    const int nb = (c->ne + E - 1) / E;
+    // optional element sub-range [sub_e0, sub_e0 + sub_ne): one element's data is contiguous, so a sub-range is a pointer offset
+    const int e0 = c->sub_ne >= 0 ? c->sub_e0 : 0, ne = c->sub_ne >= 0 ? c->sub_ne : c->ne;
+    const int nb = (ne + E - 1) / E;
     if (nb == 0) return LPF_OK;
     const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
-    CUDA_TRY(launch_ex(c->pdl_now, den ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c->stream, AFF ? c->qa : c->qd, gmap, x, y, c->ne, den, status, c->tail));
+    const double *qsrc = AFF ? c->qa + (size_t)e0 * 6 : c->qd + (size_t)e0 * C::QE;
+    CUDA_TRY(launch_ex(c->pdl_now, den ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c->stream, qsrc, gmap + (size_t)e0 * C::DP3, x, y, ne, den, status, c->tail));
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
@@ -557,6 +570,32 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
                 gc[(size_t)e * DP3 + k] = em[g] ? ~g : g;
             }
         LPF_TRY(upload(c->gmap_c, gc.data(), gc.size(), &c->bytes));
+        // plan of the pipelined host entry point: K element chunks, R dof ranges; chunk k needs the first
+        // hp_x_ranges_needed[k] ranges of x, and range j of y is final after its last-touching chunk
+        const bool ess_sorted = std::is_sorted(d->ess, d->ess + c->ness);
+        if (c->nranks == 1 && c->ndof >= (1 << 18) && c->ne >= 64 && ess_sorted) {
+            const int K = 16, R = 32;
+            const int rs = ((c->ndof + R - 1) / R + 511) & ~511;              // range size, 4 KB aligned
+            for (int j = 0; j < R; j++) if ((long)j * rs < c->ndof) c->hp_range_end.push_back((int)std::min<long>((long)(j + 1) * rs, c->ndof));
+            const int nr = (int)c->hp_range_end.size();
+            std::vector<int> last_chunk(nr, 0);
+            int run_max = 0;
+            for (int k = 0; k < K; k++) {
+                const int ea = (int)((long)c->ne * k / K), eb = (int)((long)c->ne * (k + 1) / K);
+                c->hp_elem_end.push_back(eb);
+                for (int e = ea; e < eb; e++)
+                    for (int q = 0; q < D3; q++) {
+                        const int g = d->gather[(size_t)e * D3 + q];
+                        run_max = std::max(run_max, g);
+                        last_chunk[g / rs] = k;
+                    }
+                c->hp_x_ranges_needed.push_back(run_max / rs + 1);
+            }
+            c->hp_final.assign(K, {});
+            for (int j = 0; j < nr; j++) c->hp_final[last_chunk[j]].push_back(j);
+            for (int j = 0; j < nr; j++)
+                c->hp_ess_end.push_back((int)(std::upper_bound(d->ess, d->ess + c->ness, c->hp_range_end[j] - 1) - d->ess));
+        }
         LPF_TRY(upload(c->essmask, em.data(), em.size(), &c->bytes));
         LPF_TRY(upload(c->ess, d->ess, (size_t)c->ness, &c->bytes));
     }
@@ -671,6 +710,12 @@ void lpf_destroy(lpf_ctx *c)
     if (c->state_pinned) cudaFreeHost(c->state_pinned);
     if (c->hx) cudaFreeHost(c->hx);
     if (c->hy) cudaFreeHost(c->hy);
+    for (auto e : c->hp_ev_x) cudaEventDestroy(e);
+    for (auto e : c->hp_ev_c) cudaEventDestroy(e);
+    if (c->hp_ev_start) cudaEventDestroy(c->hp_ev_start);
+    if (c->hp_ev_done) cudaEventDestroy(c->hp_ev_done);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -701,6 +746,7 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "p2p_fuse") c->p2p_fuse = (int)value;
     else if (k == "pdl") c->pdl = (int)value;
     else if (k == "affine") c->affine = (int)value;
+    else if (k == "host_pipeline") c->host_pipeline = (int)value;
     else if (k == "p2p_fuse_max") c->p2p_fuse_max = (int)value;
     else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
@@ -815,9 +861,73 @@ int lpf_apply_T(lpf_ctx *c, const double *x, double *y)
     return LPF_OK;
 }
 
+// Pipelined host-buffer apply: x streams in over the H2D copy engine in dof ranges, element chunks start as soon as the
+// ranges they read have landed, and every range of y leaves over the D2H engine as soon as its last-touching chunk is
+// done -- PCIe is full duplex, so the call costs about ONE transfer instead of H2D + apply + D2H back to back.
+static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
+{
+    const int K = (int)c->hp_elem_end.size(), R = (int)c->hp_range_end.size();
+    if (!c->s_h2d) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        c->hp_ev_x.resize(R); c->hp_ev_c.resize(K);
+        for (auto &e : c->hp_ev_x) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : c->hp_ev_c) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->hp_ev_start, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->hp_ev_done, cudaEventDisableTiming));
+    }
+    double *x = c->X, *y = c->tmp;
+    // everything enqueued so far on the context stream (earlier users of X / tmp) precedes the copies
+    CUDA_TRY(cudaEventRecord(c->hp_ev_start, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->hp_ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->hp_ev_start, 0));
+    for (int j = 0; j < R; j++) {
+        const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
+        CUDA_TRY(cudaMemcpyAsync(x + a, xh + a, sizeof(double) * (b - a), cudaMemcpyHostToDevice, c->s_h2d));
+        CUDA_TRY(cudaEventRecord(c->hp_ev_x[j], c->s_h2d));
+    }
+    CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
+    int waited = 0, rc = LPF_OK;
+    for (int k = 0; k < K && rc == LPF_OK; k++) {
+        for (; waited < c->hp_x_ranges_needed[k]; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
+        c->sub_e0 = k ? c->hp_elem_end[k - 1] : 0;
+        c->sub_ne = c->hp_elem_end[k] - c->sub_e0;
+        rc = apply_launch<false>(c, c->gmap_c, x, y, nullptr, nullptr);
+        c->sub_ne = -1;
+        if (rc != LPF_OK) break;
+        if (c->hp_final[k].empty()) continue;
+        for (int j : c->hp_final[k]) {               // essential rows of the ranges that are final now: y = x there
+            const int ea = j ? c->hp_ess_end[j - 1] : 0, eb = c->hp_ess_end[j];
+            if (eb > ea) {
+                for (; waited <= j; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
+                copy_at_kernel<<<(eb - ea + 255) / 256, 256, 0, c->stream>>>(eb - ea, c->ess + ea, x, y);
+                c->launches++;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(c->hp_ev_c[k], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->hp_ev_c[k], 0));
+        for (int j : c->hp_final[k]) {
+            const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
+            CUDA_TRY(cudaMemcpyAsync(yh + a, y + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+    }
+    // join: the context stream continues only after both copy streams are drained
+    CUDA_TRY(cudaEventRecord(c->hp_ev_done, c->s_d2h));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_done, 0));
+    CUDA_TRY(cudaEventRecord(c->hp_ev_done, c->s_h2d));
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_done, 0));
+    LPF_TRY(rc);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return LPF_OK;
+}
+
 int lpf_apply_T_host(lpf_ctx *c, const double *xh, double *yh)
 {
     if (!c || !xh || !yh) { lpf::set_error("lpf_apply_T_host: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_apply_T_host before lpf_pa_setup"); return LPF_ERR_STATE; }
+    const bool tma_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
+    if (c->host_pipeline && !c->hp_elem_end.empty() && tma_kernel) return apply_T_host_pipelined(c, xh, yh);
     const size_t nb = sizeof(double) * c->ndof;
     CUDA_TRY(cudaMemcpyAsync(c->X, xh, nb, cudaMemcpyHostToDevice, c->stream));
     LPF_TRY(lpf_apply_T(c, c->X, c->tmp));

@@ -490,4 +490,38 @@ def test_full_size_properties_big8(lpf, cuda):
     info = ctx.laplace_solve(phi, rel_tol=1e-12, max_iter=1000)
     assert info.converged and 200 <= info.iterations <= 300          # 247 at rel 1e-12
     assert np.abs(phi.cpu().numpy() - ex).max() < 1e-9 * np.abs(ex).max() * 1e3
+    # host-buffer entry point at a size where it pipelines H2D / element chunks / D2H over three streams: same result as
+    # the device-resident apply, with and without the pipeline, general and affine kernels, repeated calls
+    yd = torch.empty_like(x)
+    xh = x.cpu().pin_memory()
+    for aff in (1, 0):
+        ctx.set_option("affine", aff)
+        ctx.apply_T(x, yd)
+        ref = yd.cpu().numpy()
+        for pipe in (1, 0, 1):
+            ctx.set_option("host_pipeline", pipe)
+            yh = torch.full((sp.ndof,), np.nan, dtype=torch.float64).pin_memory()
+            ctx.apply_T_host(xh, yh)
+            assert rel_err(yh.numpy(), ref) < TOL_OP, (aff, pipe)
+    ctx.close()
+
+
+def test_host_pipeline_on_unstructured_mesh(lpf, orc, cuda):
+    """Pipelined host apply on the cylinder mesh (order 6: 727 k dofs): chunk / range dependencies come from the gather
+    map, not from any structure of the mesh."""
+    torch = cuda
+    m = lpf.Mesh.read(os.path.join(HERE, "meshes", "cylinder_half.mesh"))
+    sp = lpf.Space(m, 6)
+    assert sp.ndof > (1 << 18)
+    ctx = _ctx(lpf, torch, sp)
+    x = _dev(torch, orc.hash_noise(sp.ndof))
+    yd = torch.empty_like(x)
+    ctx.apply_T(x, yd)
+    xh = x.cpu().pin_memory()
+    yh = torch.full((sp.ndof,), np.nan, dtype=torch.float64).pin_memory()
+    ctx.apply_T_host(xh, yh)
+    assert rel_err(yh.numpy(), yd.cpu().numpy()) < TOL_OP
+    yp = torch.full((sp.ndof,), np.nan, dtype=torch.float64)          # pageable host memory also works (staged copies)
+    ctx.apply_T_host(x.cpu(), yp)
+    assert rel_err(yp.numpy(), yd.cpu().numpy()) < TOL_OP
     ctx.close()

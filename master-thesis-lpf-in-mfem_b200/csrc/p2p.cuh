@@ -269,10 +269,10 @@ __global__ void pcg_update_p2p_kernel(int n, double *__restrict__ x, double *__r
     const double alpha = st->nom / den;
     double acc = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        x[i] = fma(alpha, d[i], x[i]);
-        const double ri = fma(-alpha, ad[i], r[i]);
-        const double zi = dinv[i] * ri;
-        r[i] = ri; z[i] = zi;
+        __stcs(x + i, fma(alpha, d[i], __ldcs(x + i)));       // streaming accesses, see pcg_update_kernel
+        const double ri = fma(-alpha, ad[i], __ldcs(r + i));
+        const double zi = __ldcs(dinv + i) * ri;
+        __stcs(r + i, ri); z[i] = zi;
         if (owned[i]) acc = fma(ri, zi, acc);
     }
     __shared__ double loc;

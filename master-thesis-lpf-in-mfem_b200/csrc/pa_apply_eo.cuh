@@ -81,6 +81,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
 
     const int tid = threadIdx.x;
     const int nb = (ne + E - 1) / E;
+    const uint64_t l2pol = l2_evict_first_policy();
     const int ez = tid / LZ, q2 = tid - ez * LZ;
     const int ex = tid / LX, lx = tid - ex * LX;
     const int xdz = lx / D, xdy = lx - xdz * D;
@@ -101,10 +102,10 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
     if (tid == 0) {
         const int n0 = batch_elems(b);
         mbar_expect_tx(bar_i, (uint32_t)(n0 * DP3 * 4));
-        bulk_g2s(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i);
+        bulk_g2s_stream(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i, l2pol);
         if (!AFF) {
             mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
-            bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+            bulk_g2s_stream(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q, l2pol);
         }
     }
     // Everything above touches only constant data (gather map, q-data): under programmatic dependent launch it overlaps
@@ -150,7 +151,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
             const int n1 = batch_elems(bn);
             fence_proxy_async();
             mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
-            bulk_g2s(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt);
+            bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
         }
 
         // ---- X stage: (B_x u, G_x u) on the line (dz,dy) ----
@@ -248,7 +249,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
             const int n1 = batch_elems(bn);
             fence_proxy_async();
             mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
-            bulk_g2s(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q);
+            bulk_g2s_stream(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q, l2pol);
         }
         if (has_next) mbar_wait(bar_i + nxt, ((it + 1) >> 1) & 1);
         if (xnext) {

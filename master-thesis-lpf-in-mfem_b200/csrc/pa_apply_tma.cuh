@@ -42,6 +42,21 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Same copy with an L2 evict-first policy: q-data and gather maps are read exactly once per apply, so they should not
+// push the vectors (x gathered / y scatter-added by up to 8 elements each, and reused by the next PCG kernels) out of L2.
+__constant__ int c_l2_stream_hint = 1;      // option "l2_hint": 1 = evict-first for the streamed data, 0 = default policy
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    if (c_l2_stream_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -79,6 +94,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
 
     const int tid = threadIdx.x;
     const int nb = (ne + E - 1) / E;
+    const uint64_t l2pol = l2_evict_first_policy();
 
     const int ez = tid / LZ, q2 = tid - ez * LZ;
     const int ex = tid / LX, lx = tid - ex * LX;
@@ -101,9 +117,9 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
     if (tid == 0) {
         const int n0 = batch_elems(b);
         mbar_expect_tx(bar_i, (uint32_t)(n0 * DP3 * 4));
-        bulk_g2s(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i);
+        bulk_g2s_stream(sidx, gmap + (size_t)b * E * DP3, (uint32_t)(n0 * DP3 * 4), bar_i, l2pol);
         mbar_expect_tx(bar_q, (uint32_t)(n0 * QE * 8));
-        bulk_g2s(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q);
+        bulk_g2s_stream(sq, qd + (size_t)b * E * QE, (uint32_t)(n0 * QE * 8), bar_q, l2pol);
     }
     // Everything above touches only constant data (gather map, q-data): under programmatic dependent launch it overlaps
     // the tail of the previous kernel.  x, y and the PCG status are produced by that kernel: wait for it here.
@@ -145,7 +161,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
             const int n1 = batch_elems(bn);
             fence_proxy_async();
             mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
-            bulk_g2s(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt);
+            bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
         }
 
         // ---- X stage ----
@@ -231,7 +247,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
             const int n1 = batch_elems(bn);
             fence_proxy_async();
             mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
-            bulk_g2s(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q);
+            bulk_g2s_stream(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q, l2pol);
         }
         // x gathers of the next batch (its gather map landed long ago)
         if (has_next) mbar_wait(bar_i + nxt, ((it + 1) >> 1) & 1);

@@ -153,11 +153,13 @@ __global__ void pcg_update_kernel(int n, double *__restrict__ x, double *__restr
     }
     const double alpha = st->nom / den;
     double acc = 0.0;
+    // x, r, dinv are touched once per iteration: streaming (evict-first) accesses, so that z, d and A d -- handed from kernel
+    // to kernel inside the iteration and covered by the persisting-L2 window (pcg_l2_window) -- stay in L2
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        x[i] = fma(alpha, d[i], x[i]);
-        const double ri = fma(-alpha, ad[i], r[i]);
-        const double zi = dinv[i] * ri;
-        r[i] = ri; z[i] = zi;
+        __stcs(x + i, fma(alpha, d[i], __ldcs(x + i)));
+        const double ri = fma(-alpha, ad[i], __ldcs(r + i));
+        const double zi = __ldcs(dinv + i) * ri;
+        __stcs(r + i, ri); z[i] = zi;
         if (!owned || owned[i]) acc = fma(ri, zi, acc);
     }
     grid_sum_finalize(acc, partials, &st->counter, [&](double s) {

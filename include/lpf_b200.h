@@ -241,7 +241,19 @@ const double *lpf_phi_dev(lpf_ctx *ctx);
 int lpf_time_apply(lpf_ctx *ctx, const double *x_dev, double *y_dev, int reps, float *ms_total,
                    float *ms_kernel, long *n_launches);
 long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launched by this context so far */
-int lpf_set_option(lpf_ctx *ctx, const char *name, long value);   /* kernel variant knobs, see DESIGN.md */
+/* Tuning / A-B switches (defaults in brackets; every default is the measured best):
+ *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30-32 = even-odd (E, CTAs/SM) alternatives;
+ *                         1-5, 10-15, 100+ = earlier designs kept for re-measurement
+ *   "affine" [1]          affine fast path when every element is affine (lpf_affine_active)
+ *   "use_graph" [1], "pcg_chunk" [16]   CUDA graph of pcg_chunk CG iterations, status polled once per chunk
+ *   "pdl" [1]             programmatic dependent launch between the kernels of a CG iteration
+ *   "skip_zero_apply" [1] skip the initial-residual apply when the guess is zero off the essential dofs (exact)
+ *   "p2p_fuse" [0], "p2p_fuse_max" [2048]   halo-sum + all-reduce in the last CTA of the apply kernel (small interfaces)
+ *   "host_pipeline" [1]   lpf_apply_T_host overlaps H2D / element chunks / D2H
+ *   "l2_hint" [1], "l2_persist" [0]   evict-first hint on streamed TMA copies; persisting-L2 window over z, d, A d
+ *   "max_ctas" [0 = resident CTAs x SMs]   caps the persistent grid (tests)
+ * Environment overrides read at lpf_create: LPF_PDL, LPF_PCG_CHUNK, LPF_P2P_FUSE, LPF_P2P_FUSE_MAX, LPF_AFFINE, LPF_L2_HINT, LPF_L2_PERSIST. */
+int lpf_set_option(lpf_ctx *ctx, const char *name, long value);
 size_t lpf_device_bytes(const lpf_ctx *ctx);
 /* 1 if the affine fast path (element tensor instead of stored q-data; option "affine", on by default) is in use:
  * decided by lpf_pa_setup -- every element of the rank must be an affine hex */

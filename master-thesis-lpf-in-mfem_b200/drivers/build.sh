@@ -7,7 +7,7 @@ CXX=/usr/bin/g++
 FLAGS="-O2 -std=c++17 -Wall -I../../include -pthread"
 LINK="-L.. -llpf_b200 -Wl,-rpath,\$ORIGIN/../.. -pthread"
 mkdir -p bin
-for d in PF_linear_par_partial ss laplace_solver cylinder-diffraction; do
+for d in PF_linear_par_partial ss laplace_solver cylinder-diffraction convergence-parallel-partial; do
   $CXX $FLAGS $d.cpp $LINK -o bin/$d
 done
 $CXX $FLAGS -Istub adapter_check.cpp $LINK -o bin/adapter_check

@@ -393,6 +393,59 @@ def test_affine_fast_path(lpf, orc, cuda, tank, p):
     c2.close()
 
 
+def _time_stepper_error(lpf, torch, mesh, p, nsteps=150, rel_tol=1e-13):
+    """convergence-parallel-partial.cpp: one period in nsteps (+1) RK4 steps, nodal max error of eta / phi_fs at t = T + dt."""
+    sp = lpf.Space(mesh, p)
+    ctx = _ctx(lpf, torch, sp)
+    ctx.jacobi_setup()
+    w = lpf.wave_params()
+    dt = w["T"] / nsteps
+    ctx.rhs_setup(lpf.make_rhs_params(w, rel_tol=rel_tol, max_iter=2000))
+    xs = sp.surf_xy[:, 0]
+    coth = 1.0 / np.tanh(w["kh"])
+    eta = lambda t: 0.5 * w["H"] * np.cos(w["omega"] * t - w["k"] * xs)
+    pfs = lambda t: -0.5 * w["H"] * w["cwave"] * coth * np.sin(w["omega"] * t - w["k"] * xs)
+    sd = _dev(torch, np.concatenate([eta(0.0), pfs(0.0)]))
+    t = 0.0
+    for _ in range(nsteps + 1):
+        t = ctx.rk4_step(sd, t, dt)
+    st = sd.cpu().numpy()
+    ctx.close()
+    return sp.ndof, np.abs(st[:sp.nsurf] - eta(t)).max(), np.abs(st[sp.nsurf:] - pfs(t)).max()
+
+
+def test_time_stepper_p_convergence_known_answers(lpf, cuda):
+    """The reference's own verification (Convergence_and_Scaling/convergence-parallel-partial.cpp:150,249-305): spectral
+    p-convergence of eta after one wave period on the 3-element periodic wave-tank.mesh.  Known answers: SURVEY.md App. E
+    (restated prototype, nodal max norms) -- same digits expected to ~10 %."""
+    torch = cuda
+    known = {1: (12, 5.3e-3, 9.2e-3), 2: (54, 4.6e-4, 7.3e-4), 3: (144, 1.3e-4, 1.8e-4), 4: (300, 5.2e-6, 7.0e-6),
+             5: (540, 5.6e-7, 7.5e-7), 6: (882, 1.5e-8, 1.8e-8)}
+    prev = None
+    for p, (dofs, e_eta, e_phi) in known.items():
+        n, ee, ep = _time_stepper_error(lpf, torch, lpf.Mesh.wave_tank(3, 1, 1), p)
+        assert n == dofs
+        assert 0.8 * e_eta < ee < 1.25 * e_eta, (p, ee, e_eta)
+        assert 0.8 * e_phi < ep < 1.25 * e_phi, (p, ep, e_phi)
+        assert prev is None or ee < prev            # monotone spectral decay
+        prev = ee
+
+
+def test_time_stepper_h_convergence_known_answers(lpf, cuda):
+    """convergence-parallel-partial-hconv.cpp idea at order 4: eta error 5.2e-6 / 4.3e-7 / 3.3e-8 on 0 / 1 / 2 uniform
+    refinements, i.e. a factor >= 10 per level."""
+    torch = cuda
+    known = [(300, 5.2e-6), (1944, 4.3e-7), (13872, 3.3e-8)]
+    m = lpf.Mesh.wave_tank(3, 1, 1)
+    errs = []
+    for lvl, (dofs, e_eta) in enumerate(known):
+        n, ee, _ = _time_stepper_error(lpf, torch, m, 4)
+        assert n == dofs and 0.8 * e_eta < ee < 1.25 * e_eta, (lvl, n, ee)
+        errs.append(ee)
+        m = m.refine(1)
+    assert errs[0] / errs[1] > 10 and errs[1] / errs[2] > 10
+
+
 def test_golden_vectors(lpf, cuda):
     """Committed oracle outputs (tests/golden/tank_p3.npz, made by make_golden.py) through the
     arrays-only descriptor route an MFEM adapter would take."""

@@ -65,7 +65,9 @@ cudaError_t launch_ex(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, s
 
 inline int vec_grid(int n, int sm_count)
 {
-    const int need = (n + 255) / 256;
+    // >= 4 entries per thread: on small vectors the cost of a reducing kernel is its tail (one atomic per block on the
+    // "last block" counter + the final sum over the block partials), so fewer, fatter blocks; large vectors fill 8 x SMs
+    const int need = (n + 1023) / 1024;
     return std::max(1, std::min(need, std::min(sm_count * 8, LPF_MAX_PARTIALS)));
 }
 
@@ -502,6 +504,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     if (const char *e = std::getenv("LPF_PCG_CHUNK")) c->chunk = std::max(1, std::atoi(e));
     if (const char *e = std::getenv("LPF_P2P_FUSE")) c->p2p_fuse = std::atoi(e);
     if (const char *e = std::getenv("LPF_AFFINE")) c->affine = std::atoi(e);
+    if (const char *e = std::getenv("LPF_APPLY_VARIANT")) c->variant = std::atoi(e);
     if (const char *e = std::getenv("LPF_L2_PERSIST")) c->l2_persist = std::atoi(e);
     if (const char *e = std::getenv("LPF_L2_HINT")) { const int v = std::atoi(e); CUDA_TRY(cudaMemcpyToSymbol(c_l2_stream_hint, &v, sizeof(int))); }
     if (const char *e = std::getenv("LPF_P2P_FUSE_MAX")) c->p2p_fuse_max = std::atoi(e);

@@ -33,7 +33,7 @@ inline void check(int rc, const char *what)
 
 /// Builds the plain descriptor the device context needs from MFEM objects (SURVEY.md 8b last row).
 struct SpaceDescBuilder {
-    std::vector<double> jac;
+    std::vector<double> jac, corners;
     std::vector<int> gather, ess, surf2vol, surf_elems, surf_mult;
     std::vector<double> surf_xy;
     lpf_space_desc desc{};
@@ -60,8 +60,27 @@ struct SpaceDescBuilder {
         ess.assign(ess_tdof_list.GetData(), ess_tdof_list.GetData() + ess_tdof_list.Size());
         surf2vol.assign(surf_vdofs.GetData(), surf_vdofs.GetData() + surf_vdofs.Size());
         surf_xy.assign(surf_coords.GetData(), surf_coords.GetData() + surf_coords.Size());
+        // Geometry of GetDerivative (and of the affine fast path): the 8 corners of every hex, lexicographic, from the mesh
+        // transformation -- valid for the trilinear meshes the reference ships (vertex coordinates alone would be wrong on
+        // its periodic meshes, whose geometry lives in the L2 nodes).  [MFEM] ElementTransformation::Transform
+        corners.resize((size_t)ne * 24);
+        {
+            double buf[3] = {0, 0, 0};
+            mfem::Vector pt(buf, 3);
+            for (int e = 0; e < ne; e++) {
+                mfem::ElementTransformation *T = fes.GetMesh()->GetElementTransformation(e);
+                for (int c = 0; c < 8; c++) {
+                    mfem::IntegrationPoint ip;
+                    ip.Set3(c & 1, (c >> 1) & 1, (c >> 2) & 1);
+                    T->Transform(ip, pt);
+                    for (int a = 0; a < 3; a++) corners[(size_t)e * 24 + c * 3 + a] = buf[a];
+                }
+            }
+        }
         desc.order = p; desc.ne = ne; desc.ndof = fes.GetVSize();
-        desc.corners = nullptr; desc.jac = jac.data(); desc.gather = gather.data();
+        // q-data from MFEM's own Jacobians (curved meshes included); corners serve the surface derivative.  Pass
+        // desc.jac = nullptr instead to let the library build q-data from the corners and enable its affine fast path.
+        desc.corners = corners.data(); desc.jac = jac.data(); desc.gather = gather.data();
         desc.n_ess = (int)ess.size(); desc.ess = ess.data();
         desc.n_surf = (int)surf2vol.size(); desc.surf2vol = surf2vol.data(); desc.surf_xy = surf_xy.data();
         desc.nranks = 1; desc.rank = 0;

@@ -91,9 +91,19 @@ public:
     Vector J;
 };
 
+class IntegrationPoint {
+public:
+    double x = 0, y = 0, z = 0;
+    void Set3(double a, double b, double c) { x = a; y = b; z = c; }
+};
+class ElementTransformation {
+public:
+    void Transform(const IntegrationPoint &, Vector &) {}
+};
 class Mesh {
 public:
     const GeometricFactors *GetGeometricFactors(const IntegrationRule &, int) { static GeometricFactors g; return &g; }
+    ElementTransformation *GetElementTransformation(int) { static ElementTransformation t; return &t; }
 };
 
 class FiniteElement {

@@ -582,7 +582,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         // plan of the pipelined host entry point: K element chunks, R dof ranges; chunk k needs the first
         // hp_x_ranges_needed[k] ranges of x, and range j of y is final after its last-touching chunk
         const bool ess_sorted = std::is_sorted(d->ess, d->ess + c->ness);
-        if (c->nranks == 1 && c->ndof >= (1 << 18) && c->ne >= 64 && ess_sorted) {
+        if (c->ndof >= (1 << 18) && c->ne >= 64 && ess_sorted) {
             const int K = 16, R = 32;
             const int rs = ((c->ndof + R - 1) / R + 511) & ~511;              // range size, 4 KB aligned
             for (int j = 0; j < R; j++) if ((long)j * rs < c->ndof) c->hp_range_end.push_back((int)std::min<long>((long)(j + 1) * rs, c->ndof));
@@ -600,7 +600,10 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
                     }
                 c->hp_x_ranges_needed.push_back(run_max / rs + 1);
             }
-            c->hp_final.assign(K, {});
+            // multi-GPU: ranges holding dofs shared with other ranks are final only after the halo-sum that follows the
+            // last chunk (group K); with local dofs numbered by global id these are the few ranges at both ends of a slab
+            for (int i = 0; i < d->n_shared; i++) last_chunk[d->shared_dofs[i] / rs] = K;
+            c->hp_final.assign(K + 1, {});
             for (int j = 0; j < nr; j++) c->hp_final[last_chunk[j]].push_back(j);
             for (int j = 0; j < nr; j++)
                 c->hp_ess_end.push_back((int)(std::upper_bound(d->ess, d->ess + c->ness, c->hp_range_end[j] - 1) - d->ess));
@@ -927,6 +930,25 @@ static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
             const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
             CUDA_TRY(cudaMemcpyAsync(yh + a, y + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, c->s_d2h));
         }
+    }
+    if (rc == LPF_OK && !c->hp_final[K].empty()) {   // multi-GPU: halo-sum, then the ranges that hold shared dofs
+        rc = halo_sum(c, c->halo, y);
+        for (int j : c->hp_final[K]) {
+            const int ea = j ? c->hp_ess_end[j - 1] : 0, eb = c->hp_ess_end[j];
+            if (eb > ea && rc == LPF_OK) {
+                for (; waited <= j; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
+                copy_at_kernel<<<(eb - ea + 255) / 256, 256, 0, c->stream>>>(eb - ea, c->ess + ea, x, y);
+                c->launches++;
+            }
+        }
+        CUDA_TRY(cudaEventRecord(c->hp_ev_done, c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->hp_ev_done, 0));
+        for (int j : c->hp_final[K]) {
+            const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
+            CUDA_TRY(cudaMemcpyAsync(yh + a, y + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+    } else if (rc == LPF_OK && c->nranks > 1) {
+        rc = halo_sum(c, c->halo, y);                // a rank without shared dofs still takes part in the exchange
     }
     // join: the context stream continues only after both copy streams are drained
     CUDA_TRY(cudaEventRecord(c->hp_ev_done, c->s_d2h));

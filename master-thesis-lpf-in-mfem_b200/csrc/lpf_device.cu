@@ -216,6 +216,7 @@ int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, 
         CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
         if (bps < 1) bps = 1;
+        if (std::getenv("LPF_VERBOSE")) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, C::NT, (size_t)C::SMEM_BYTES, bps);
     }
     // optional element sub-range [sub_e0, sub_e0 + sub_ne): one element's data is contiguous, so a sub-range is a pointer offset
     const int e0 = c->sub_ne >= 0 ? c->sub_e0 : 0, ne = c->sub_ne >= 0 ? c->sub_ne : c->ne;
@@ -292,7 +293,7 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
                 case 1: if (v == 31) LPF_EO(1, 32, 2); LPF_EO(1, 16, 3);
                 case 2: if (v == 31) LPF_EO(2, 16, 2); LPF_EO(2, 8, 3);
                 case 3: if (v == 31) LPF_EO(3, 8, 2); LPF_EO(3, 5, 3);
-                case 4: if (v == 31) LPF_EO(4, 4, 3); if (v == 32) LPF_EO(4, 2, 5); LPF_EO(4, 3, 3);
+                case 4: if (v == 31) LPF_EO(4, 4, 3); if (v == 32) LPF_EO(4, 2, 5); if (v == 33) LPF_EO(4, 3, 4); LPF_EO(4, 3, 3);
                 case 5: if (v == 31) LPF_EO(5, 3, 2); if (v == 32) LPF_EO(5, 2, 4); LPF_EO(5, 2, 3);
                 case 6: if (v == 31) LPF_EO(6, 3, 1); if (v == 32) LPF_EO(6, 2, 3); LPF_EO(6, 2, 2);
                 case 7: if (v == 31) LPF_EO(7, 1, 2); if (v == 32) LPF_EO(7, 2, 2); LPF_EO(7, 2, 1);
@@ -505,6 +506,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     if (const char *e = std::getenv("LPF_P2P_FUSE")) c->p2p_fuse = std::atoi(e);
     if (const char *e = std::getenv("LPF_AFFINE")) c->affine = std::atoi(e);
     if (const char *e = std::getenv("LPF_APPLY_VARIANT")) c->variant = std::atoi(e);
+    if (const char *e = std::getenv("LPF_MAX_CTAS")) c->max_ctas = std::atoi(e);
     if (const char *e = std::getenv("LPF_L2_PERSIST")) c->l2_persist = std::atoi(e);
     if (const char *e = std::getenv("LPF_L2_HINT")) { const int v = std::atoi(e); CUDA_TRY(cudaMemcpyToSymbol(c_l2_stream_hint, &v, sizeof(int))); }
     if (const char *e = std::getenv("LPF_P2P_FUSE_MAX")) c->p2p_fuse_max = std::atoi(e);

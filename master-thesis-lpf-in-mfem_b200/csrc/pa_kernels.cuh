@@ -96,13 +96,15 @@ struct ApplyCfg {
     // stores (fixed qx, consecutive lines) and the Y-stage loads (fixed dy, consecutive (dz,qx)) spread
     // over the 16 eight-byte bank pairs.
     static constexpr int SAY = (Q & 1) ? Q : Q + 1;
-    static constexpr int SAZ = lpf_pad_to(D * SAY, Q);
+    // order 4: unpadded dz stride (tools/smem_layout_sim.py: 322 instead of 319 wavefronts per element, 920 instead of 951
+    // doubles) -- 3 elements + q-data + maps then take 56.3 KB and FOUR CTAs fit one SM instead of three
+    static constexpr int SAZ = (P == 4) ? D * SAY : lpf_pad_to(D * SAY, Q);
     static constexpr int SAA = D * SAZ;
     // smem B: [arr 3][dz][qy][qx]; dz stride == Q (mod 16)
     static constexpr int SBZ = lpf_pad_to(Q * Q, Q);
     static constexpr int SBA = D * SBZ;
     static constexpr int ES_RAW = 2 * SAA + 3 * SBA;
-    static constexpr int ES = ES_RAW | 1;          // odd element stride
+    static constexpr int ES = (P == 4) ? ES_RAW : (ES_RAW | 1);          // odd element stride (order 4: see SAZ)
     static constexpr int OFFB = 2 * SAA;
     static constexpr size_t SMEM_BYTES = (size_t)E * ES * sizeof(double);
 };

@@ -292,7 +292,7 @@ int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double
             switch (c->p) {
                 case 1: if (v == 31) LPF_EO(1, 32, 2); LPF_EO(1, 16, 3);
                 case 2: if (v == 31) LPF_EO(2, 16, 2); LPF_EO(2, 8, 3);
-                case 3: if (v == 31) LPF_EO(3, 8, 2); LPF_EO(3, 5, 3);
+                case 3: if (v == 31) LPF_EO(3, 8, 2); if (v == 33) LPF_EO(3, 7, 3); if (v == 34) LPF_EO(3, 5, 4); LPF_EO(3, 5, 3);
                 case 4: if (v == 31) LPF_EO(4, 4, 3); if (v == 32) LPF_EO(4, 2, 5); if (v == 33) LPF_EO(4, 3, 4); LPF_EO(4, 3, 3);
                 case 5: if (v == 31) LPF_EO(5, 3, 2); if (v == 32) LPF_EO(5, 2, 4); LPF_EO(5, 2, 3);
                 case 6: if (v == 31) LPF_EO(6, 3, 1); if (v == 32) LPF_EO(6, 2, 3); LPF_EO(6, 2, 2);

@@ -86,27 +86,33 @@ __global__ void pa_affine_setup_kernel(int ne, const double *__restrict__ corner
     q[5] = s * (A31 * A31 + A32 * A32 + A33 * A33);
 }
 
+// Strides of the two stage buffers, per order, picked by the bank-conflict model tools/smem_layout_sim.py (shared-memory
+// wavefronts per element, old formula-padded layout -> this table):  p1 48 -> 32, p2 90 -> 63, p3 230 -> 167, p4 319 -> 322
+// (smaller: 4 CTAs per SM), p5 560 -> 496, p6 680 -> 642, p7 1006 -> 862, p8 1394 -> 1394 (smaller).  Measured at order 3:
+// 77 % -> 89 % of the HBM roofline from the layout alone.
+//   {SAY, SAZ, SBZ, PAD}: A = [arr 2][dz][dy][qx] with strides SAZ, SAY, 1; B = [arr 3][dz][qy][qx] with strides SBZ, Q, 1
+__host__ __device__ constexpr int lpf_smem_stride(int p, int which)
+{
+    constexpr int T[9][4] = {{0, 0, 0, 0}, {4, 8, 12, 1}, {5, 20, 20, 0}, {5, 28, 26, 1}, {7, 35, 38, 0},
+                             {7, 42, 55, 0}, {9, 72, 72, 0}, {10, 89, 89, 0}, {10, 90, 106, 0}};
+    return T[p][which];
+}
+
 template <int P, int E>
 struct ApplyCfg {
     static constexpr int D = P + 1, Q = P + 2;
     static constexpr int LX = D * D, LY = D * Q, LZ = Q * Q;
     static constexpr int NT = E * LZ;
     static constexpr int DP3 = (D * D * D + 3) & ~3;    // gather-map row stride (rows padded to 16 bytes for bulk copies)
-    // smem A: [arr 2][dz][dy][qx]; dy stride odd, dz stride == Q (mod 16) so that both the X-stage
-    // stores (fixed qx, consecutive lines) and the Y-stage loads (fixed dy, consecutive (dz,qx)) spread
-    // over the 16 eight-byte bank pairs.
-    static constexpr int SAY = (Q & 1) ? Q : Q + 1;
-    // order 4: unpadded dz stride (tools/smem_layout_sim.py: 322 instead of 319 wavefronts per element, 920 instead of 951
-    // doubles) -- 3 elements + q-data + maps then take 56.3 KB and FOUR CTAs fit one SM instead of three
-    static constexpr int SAZ = (P == 4) ? D * SAY : lpf_pad_to(D * SAY, Q);
+    static constexpr int SAY = lpf_smem_stride(P, 0);
+    static constexpr int SAZ = lpf_smem_stride(P, 1);
     static constexpr int SAA = D * SAZ;
-    // smem B: [arr 3][dz][qy][qx]; dz stride == Q (mod 16)
-    static constexpr int SBZ = lpf_pad_to(Q * Q, Q);
+    static constexpr int SBZ = lpf_smem_stride(P, 2);
     static constexpr int SBA = D * SBZ;
-    static constexpr int ES_RAW = 2 * SAA + 3 * SBA;
-    static constexpr int ES = (P == 4) ? ES_RAW : (ES_RAW | 1);          // odd element stride (order 4: see SAZ)
+    static constexpr int ES = 2 * SAA + 3 * SBA + lpf_smem_stride(P, 3);      // element stride
     static constexpr int OFFB = 2 * SAA;
     static constexpr size_t SMEM_BYTES = (size_t)E * ES * sizeof(double);
+    static_assert(SAY >= Q && SAZ >= D * SAY - (SAY - Q) && SBZ >= Q * Q, "stage-buffer strides too small");
 };
 
 __device__ __forceinline__ double2 ldg_stream2(const double2 *p)

@@ -2,8 +2,9 @@
 
 For every unrolled LDS/STS instruction of a stage it lists the 8-byte word index each active lane touches,
 splits the warp into two half-warps (64-bit accesses are served 16 lanes at a time) and counts wavefronts as
-max over the 16 bank pairs of the number of distinct words.  Used to pick the paddings in ApplyCfg
-(csrc/pa_kernels.cuh); `python tools/smem_layout_sim.py 4 2` prints the wavefronts per element.
+max over the 16 bank pairs of the number of distinct words.  Used to pick the per-order stride table
+lpf_smem_stride() in csrc/pa_kernels.cuh; `python tools/smem_layout_sim.py 4 2` prints the wavefronts per element of the OLD
+formula-padded layout ("current") and the best layouts of the searched family.
 """
 import itertools
 import sys

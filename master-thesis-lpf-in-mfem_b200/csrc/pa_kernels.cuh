@@ -93,8 +93,8 @@ __global__ void pa_affine_setup_kernel(int ne, const double *__restrict__ corner
 //   {SAY, SAZ, SBZ, PAD}: A = [arr 2][dz][dy][qx] with strides SAZ, SAY, 1; B = [arr 3][dz][qy][qx] with strides SBZ, Q, 1
 __host__ __device__ constexpr int lpf_smem_stride(int p, int which)
 {
-    constexpr int T[9][4] = {{0, 0, 0, 0}, {4, 8, 12, 1}, {5, 20, 20, 0}, {5, 28, 26, 1}, {7, 35, 38, 0},
-                             {7, 42, 55, 0}, {9, 72, 72, 0}, {10, 89, 89, 0}, {10, 90, 106, 0}};
+    constexpr int T[9][4] = {{0, 0, 0, 0}, {4, 8, 12, 1}, {5, 20, 20, 0}, {5, 28, 26, 1}, {7, 35, 38, 12},
+                             {7, 42, 55, 4}, {9, 72, 72, 0}, {10, 89, 89, 0}, {10, 90, 106, 0}};
     return T[p][which];
 }
 

@@ -128,6 +128,25 @@ def cpu_apply_gdofs(order, refine, seconds=12.0, threads=None):
     return sp.ndof * n / el / 1e9, nthreads, f"{n} applies on wave-tank-big8 r={refine} order={order} ({sp.ne} hexes, {sp.ndof} dofs)", el / n
 
 
+def cpu_pcg_ms_per_iteration(order, refine, iters=40, threads=None):
+    """Second half of the metric on the CPU: the C restatement's Jacobi-PCG (same loop and stopping rule) on the tank of the
+    GPU's RK4 leg, capped at `iters` iterations (a bounded sample: a full RK4 step is 4 x 374 of them)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c                                 # checker / baseline only
+    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
+    oracle_c.set_threads(threads or os.cpu_count())
+    sp = lpf.Space(lpf.Mesh.wave_tank(128, 2, 16).refine(refine), order)
+    cop = oracle_c.COperator(order, sp.corners, sp.gather, sp.ndof, lpf.basis_tables(order))
+    dinv = 1.0 / cop.diag()
+    dinv[sp.ess] = 1.0
+    x = np.zeros(sp.ndof)
+    x[sp.surf2vol] = np.cos(2 * np.pi * sp.surf_xy[:, 0])
+    t0 = time.perf_counter()
+    _, info = cop.pcg(np.sort(sp.ess), dinv, x, 1e-12, 0.0, iters)
+    el = time.perf_counter() - t0
+    return 1e3 * el / max(1, info["applies"] - 1), info["iterations"]
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -143,6 +162,12 @@ def run_reference(a):
             "cpu_baseline": {"value": g, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
             "e2e": {"value": g, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "MFEM/hypre/MPI are not installable here; this is the C/OpenMP restatement of MFEM's CPU PA path (oracle/pa_oracle.c)"}
+    try:
+        ms_it, nit = cpu_pcg_ms_per_iteration(a.order, a.rk4_refine)
+        line["cpu_baseline"]["pcg_ms_per_cg_iteration"] = ms_it
+        line["cpu_baseline"]["pcg_sample"] = f"{nit} Jacobi-PCG iterations on wave-tank-big8 r={a.rk4_refine} order={a.order}"
+    except Exception as e:
+        line["cpu_baseline"]["pcg_error"] = str(e)[:200]
     print(json.dumps(line), flush=True)
 
 
@@ -296,6 +321,12 @@ def run_ours(a):
     if not a.no_cpu:
         g, nth, sample, _ = cpu_apply_gdofs(p, min(a.refine, 1), seconds=12.0)
         line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample}
+        try:
+            ms_it, nit = cpu_pcg_ms_per_iteration(p, a.rk4_refine)
+            line["cpu_baseline"]["pcg_ms_per_cg_iteration"] = ms_it
+            line["cpu_baseline"]["pcg_sample"] = f"{nit} Jacobi-PCG iterations on wave-tank-big8 r={a.rk4_refine} order={p} (the RK4 leg's mesh; a step is 4 solves)"
+        except Exception as e:                      # the baseline must never take the GPU numbers down with it
+            line["cpu_baseline"]["pcg_error"] = str(e)[:200]
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

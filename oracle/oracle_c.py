@@ -61,6 +61,14 @@ class COperator:
                         ip(self.offsets), ip(self.indices), dp(x), dp(y))
         return y
 
+    def mult_n(self, x, reps):
+        """reps applies with the work buffers allocated once (timing entry of the CPU baseline); returns the last y."""
+        y = np.zeros(self.ndof)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        lib.lpf_or_mult_n(self.ne, self.p, self.ndof, dp(self.B), dp(self.G), dp(self.qd), ip(self.gather),
+                          ip(self.offsets), ip(self.indices), dp(x), dp(y), int(reps))
+        return y
+
     def apply_E(self, xE):
         xE = np.ascontiguousarray(xE, dtype=np.float64)
         yE = np.zeros_like(xE)

@@ -292,6 +292,19 @@ void lpf_or_mult(int ne, int p, int ndof, const double *B, const double *G, cons
     free(op.xE); free(op.yE);
 }
 
+/* reps applies with the E-vector work buffers allocated ONCE (what MFEM's operator does): the timing entry of the CPU
+ * baseline -- lpf_or_mult() above pays two 32 MB malloc + first-touch page faults per call, which is not the algorithm */
+void lpf_or_mult_n(int ne, int p, int ndof, const double *B, const double *G, const double *qd,
+                   const int *gather, const int *offsets, const int *indices, const double *x, double *y, int reps)
+{
+    const int D3 = (p + 1) * (p + 1) * (p + 1);
+    lpf_or_op op = {ne, p, ndof, 0, B, G, qd, gather, offsets, indices, NULL, NULL, NULL, NULL, 0};
+    op.xE = (double *)malloc(sizeof(double) * (size_t)ne * D3);
+    op.yE = (double *)malloc(sizeof(double) * (size_t)ne * D3);
+    for (int r = 0; r < reps; r++) op_mult_raw(&op, x, y);
+    free(op.xE); free(op.yE);
+}
+
 /* FormLinearSystem(ess, x, b=0) + Jacobi-PCG.  On entry x holds the essential values on `ess`
  * (other entries ignored: the interior of the initial guess is zeroed, copy_interior = 0);
  * on exit x is the solution.  info[0]=iterations, info[1]=converged, info[2]=final (r,Mr)^1/2,

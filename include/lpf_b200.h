@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LPF_B200_VERSION 100
+#define LPF_B200_VERSION 200
 
 typedef enum {
     LPF_OK = 0,
@@ -181,6 +181,10 @@ int lpf_apply_T(lpf_ctx *ctx, const double *x_dev, double *y_dev);
 int lpf_apply_T_host(lpf_ctx *ctx, const double *x_host, double *y_host);
 /* a2  BilinearForm::AssembleDiagonal (DiffusionIntegrator::AssembleDiagonalPA + G^T + P^T) */
 int lpf_diag(lpf_ctx *ctx, double *diag_dev);
+/* a2  DiffusionIntegrator::AssembleDiagonalPA(Vector &diag): the E-vector diagonal [ne][D^3], ACCUMULATED into diagE_dev
+ * (MFEM's semantics; the form then applies the restriction-transpose and P^T).  This is the call
+ * OperatorJacobiSmoother(*a_loc_cach, ess_tdof) reaches through the integrator                        (:124) */
+int lpf_pa_diag_E(lpf_ctx *ctx, double *diagE_dev);
 /* a2  OperatorJacobiSmoother(a, ess_tdof): dinv = 1/diag, dinv[ess] = 1              (:124) */
 int lpf_jacobi_setup(lpf_ctx *ctx);
 int lpf_jacobi_dinv(lpf_ctx *ctx, double *dinv_dev);
@@ -241,18 +245,23 @@ const double *lpf_phi_dev(lpf_ctx *ctx);
 int lpf_time_apply(lpf_ctx *ctx, const double *x_dev, double *y_dev, int reps, float *ms_total,
                    float *ms_kernel, long *n_launches);
 long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launched by this context so far */
-/* Tuning / A-B switches (defaults in brackets; every default is the measured best):
- *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30-32 = even-odd (E, CTAs/SM) alternatives;
- *                         1-5, 10-15, 100+ = earlier designs kept for re-measurement
+/* Options (defaults in brackets; every default is the measured best):
+ *   "deterministic" [0]   1 = bit-reproducible results: the restriction-transpose is an ordered gather (element order, as
+ *                         MFEM's CPU ElementRestriction::MultTranspose) of an E-vector instead of red.global.add, the
+ *                         diagonal likewise; CG iteration counts are then identical from run to run.  ~20 % slower apply.
+ *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30-34 = alternative (E, CTAs/SM) pairs
  *   "affine" [1]          affine fast path when every element is affine (lpf_affine_active)
  *   "use_graph" [1], "pcg_chunk" [16]   CUDA graph of pcg_chunk CG iterations, status polled once per chunk
  *   "pdl" [1]             programmatic dependent launch between the kernels of a CG iteration
  *   "skip_zero_apply" [1] skip the initial-residual apply when the guess is zero off the essential dofs (exact)
- *   "p2p_fuse" [0], "p2p_fuse_max" [2048]   halo-sum + all-reduce in the last CTA of the apply kernel (small interfaces)
+ *   "p2p_fuse" [2]        multi-GPU halo-sum of an apply: 0 = separate LL kernel, 1 = last CTA of the apply kernel (only while
+ *                         the interface has <= "p2p_fuse_max" [2048] entries), 2 = inside the apply kernel, overlapped with the
+ *                         interior elements
  *   "host_pipeline" [1]   lpf_apply_T_host overlaps H2D / element chunks / D2H
- *   "l2_hint" [1], "l2_persist" [0]   evict-first hint on streamed TMA copies; persisting-L2 window over z, d, A d
+ *   "l2_persist" [0]      persisting-L2 window over z, d, A d
  *   "max_ctas" [0 = resident CTAs x SMs]   caps the persistent grid (tests)
- * Environment overrides read at lpf_create: LPF_PDL, LPF_PCG_CHUNK, LPF_P2P_FUSE, LPF_P2P_FUSE_MAX, LPF_AFFINE, LPF_L2_HINT, LPF_L2_PERSIST. */
+ *   "verbose" [0]         print the launch geometry of every apply kernel once
+ * The library reads no environment variables (a -DLPF_DEBUG_ENV developer build maps LPF_<OPTION> onto these). */
 int lpf_set_option(lpf_ctx *ctx, const char *name, long value);
 size_t lpf_device_bytes(const lpf_ctx *ctx);
 /* 1 if the affine fast path (element tensor instead of stored q-data; option "affine", on by default) is in use:

@@ -113,6 +113,7 @@ SIGNATURES = {
     "lpf_apply_T": (C.c_int, [_VP, _VP, _VP]),
     "lpf_apply_T_host": (C.c_int, [_VP, _VP, _VP]),
     "lpf_diag": (C.c_int, [_VP, _VP]),
+    "lpf_pa_diag_E": (C.c_int, [_VP, _VP]),
     "lpf_jacobi_setup": (C.c_int, [_VP]),
     "lpf_jacobi_dinv": (C.c_int, [_VP, _VP]),
     "lpf_pcg": (C.c_int, [_VP, _VP, _VP, C.c_double, C.c_double, C.c_int, C.POINTER(PcgInfo)]),
@@ -420,6 +421,9 @@ class Context:
 
     def diag(self, out):
         _check(lib.lpf_diag(self.h, _ptr(out)), "lpf_diag")
+
+    def pa_diag_E(self, out):
+        _check(lib.lpf_pa_diag_E(self.h, _ptr(out)), "lpf_pa_diag_E")
 
     def jacobi_setup(self):
         _check(lib.lpf_jacobi_setup(self.h), "lpf_jacobi_setup")

@@ -1,0 +1,116 @@
+// Configuration, per-order coefficient tables and TMA helpers shared by the PA apply kernels.  One translation unit per
+// order (apply_order.cu compiled with -DLPF_ORDER=p) includes this file, so the __constant__ tables below exist once
+// per order and hold that order only.
+#pragma once
+#include "apply_api.hpp"
+#include "dev_util.cuh"
+#include "p2p_dev.cuh"
+
+__host__ __device__ constexpr int lpf_pad_to(int v, int target_mod16)
+{
+    // smallest w >= v with w % 16 == target_mod16 % 16
+    int w = v;
+    while ((w & 15) != (target_mod16 & 15)) w++;
+    return w;
+}
+
+// Strides of the two stage buffers, per order, picked by the bank-conflict model tools/smem_layout_sim.py (shared-memory
+// wavefronts per element, old formula-padded layout -> this table):  p1 48 -> 32, p2 90 -> 63, p3 230 -> 167, p4 319 -> 322
+// (smaller: 4 CTAs per SM), p5 560 -> 496, p6 680 -> 642, p7 1006 -> 862, p8 1394 -> 1394 (smaller).  Measured at order 3:
+// 77 % -> 89 % of the HBM roofline from the layout alone.  Orders 9, 10: formula (odd strides), not tuned.
+//   {SAY, SAZ, SBZ, PAD}: A = [arr 2][dz][dy][qx] with strides SAZ, SAY, 1; B = [arr 3][dz][qy][qx] with strides SBZ, Q, 1
+__host__ __device__ constexpr int lpf_smem_stride(int p, int which)
+{
+    constexpr int T[11][4] = {{0, 0, 0, 0}, {4, 8, 12, 1}, {5, 20, 20, 0}, {5, 28, 26, 1}, {7, 35, 38, 12},
+                              {7, 42, 55, 4}, {9, 72, 72, 0}, {10, 89, 89, 0}, {10, 90, 106, 0}, {11, 111, 123, 0}, {13, 145, 145, 0}};
+    return T[p][which];
+}
+
+template <int P, int E>
+struct ApplyCfg {
+    static constexpr int D = P + 1, Q = P + 2;
+    static constexpr int LX = D * D, LY = D * Q, LZ = Q * Q;
+    static constexpr int NT = E * LZ;
+    static constexpr int D3 = D * D * D;
+    static constexpr int DP3 = (D * D * D + 3) & ~3;    // gather-map row stride (rows padded to 16 bytes for bulk copies)
+    static constexpr int SAY = lpf_smem_stride(P, 0);
+    static constexpr int SAZ = lpf_smem_stride(P, 1);
+    static constexpr int SAA = D * SAZ;
+    static constexpr int SBZ = lpf_smem_stride(P, 2);
+    static constexpr int SBA = D * SBZ;
+    static constexpr int ES = 2 * SAA + 3 * SBA + lpf_smem_stride(P, 3);      // element stride
+    static constexpr int OFFB = 2 * SAA;
+    static constexpr size_t SMEM_BYTES = (size_t)E * ES * sizeof(double);
+    static_assert(SAY >= Q && SAZ >= D * SAY - (SAY - Q) && SBZ >= Q * Q, "stage-buffer strides too small");
+};
+
+template <int P, int E, bool AFF = false>      // AFF: affine fast path, no q-data staging area (pa_apply_eo.cuh)
+struct TmaCfg : ApplyCfg<P, E> {
+    using B = ApplyCfg<P, E>;
+    static constexpr int QE = 6 * B::Q * B::Q * B::Q;               // doubles of q-data per element
+    // byte offsets inside dynamic shared memory
+    static constexpr size_t OFF_Q = 0;                                                  // [E][QE] doubles (16B aligned)
+    static constexpr size_t OFF_IDX = OFF_Q + (AFF ? (size_t)0 : (size_t)E * QE * 8);   // [2][E][DP3] ints
+    static constexpr size_t OFF_WORK = (OFF_IDX + (size_t)2 * E * B::DP3 * 4 + 15) & ~(size_t)15;
+    static constexpr size_t OFF_BAR = (OFF_WORK + (size_t)E * B::ES * 8 + 15) & ~(size_t)15;   // 3 mbarriers
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
+};
+
+// ---- per-order coefficient tables ----------------------------------------------------------------------------------
+// {B, G} interleaved per (q, d): one 16-byte uniform load (LDCU.128) feeds both FMAs that a stage issues on the same
+// (q, d) pair.  Even / odd half tables of the (anti)symmetric B and G: see pa_apply_eo.cuh.
+template <int P>
+struct __align__(16) LpfOrderTab {
+    static constexpr int D = P + 1, Q = P + 2, MH = (Q + 1) / 2;
+    double BG[2 * Q * D];
+    double qwts[Q + (Q & 1)];
+    double BeF[MH * MH], BoF[MH * MH], GeF[MH * MH], GoF[MH * MH];   // [QC][DC], [QC][DH]
+    double BeT[MH * MH], BoT[MH * MH], GeT[MH * MH], GoT[MH * MH];   // [DC][QC], [DC][QH]
+};
+
+#ifdef LPF_ORDER
+// two slots: the kernels address slot (it >> 30) with `it` the batch counter -- always slot 0, but loop-variant, which
+// keeps the compiler from hoisting all coefficients out of the batch loop (pa_apply_tma.cuh)
+static __constant__ LpfOrderTab<LPF_ORDER> c_ot[2];
+#endif
+
+// ---- TMA 1-D bulk copies + mbarriers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+// L2 evict-first policy for the streamed data: q-data and gather maps are read exactly once per apply, so they should not
+// push the vectors (x gathered / y scatter-added by up to 8 elements each, and reused by the next PCG kernels) out of L2
+// (measured: -3 % per CG iteration at 2.25 M dofs).
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_g2s_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}

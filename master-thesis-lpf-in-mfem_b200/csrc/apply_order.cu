@@ -1,0 +1,162 @@
+// One order of the PA apply kernels: compiled once per order with -DLPF_ORDER=p (build.sh), see apply_api.hpp.
+#ifndef LPF_ORDER
+#error "compile with -DLPF_ORDER=<p>"
+#endif
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "apply_api.hpp"
+#include "pa_apply_eo.cuh"
+#include "pa_apply_evec.cuh"
+#include "pa_apply_tma.cuh"
+
+#define LPF_CAT_(a, b) a##b
+#define LPF_CAT(a, b) LPF_CAT_(a, b)
+
+namespace {
+
+constexpr int P = LPF_ORDER;
+
+template <int E, int MINB, bool EO, bool AFF = false, bool DET = false>
+int launch_persistent(LpfApplyArgs &a)
+{
+    using C = TmaCfg<P, E, AFF>;
+    static int blocks_per_sm[16] = {0};
+    void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs);
+    if constexpr (EO) { kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET>; }
+    else { kd = pa_apply_tma_kernel<P, E, true, MINB, DET>; kn = pa_apply_tma_kernel<P, E, false, MINB, DET>; }
+    int &bps = blocks_per_sm[a.dev & 15];
+    if (bps == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
+        if (bps < 1) bps = 1;
+        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, C::NT, (size_t)C::SMEM_BYTES, bps);
+    }
+    const int nb = (a.k.ne + E - 1) / E;
+    a.threads = C::NT; a.smem = C::SMEM_BYTES; a.grid = 0;
+    if (nb == 0) return LPF_OK;
+    int grid = std::min(nb, a.max_ctas > 0 ? a.max_ctas : bps * a.sm_count);
+    grid = std::min(grid, LPF_DEN_SLOTS);            // one (d, A d) slot per CTA
+    a.grid = grid;
+    if (a.k.tail.mode == 2) a.k.tail.n_if_batches = (a.k.tail.n_if_batches + E - 1) / E;     // elements -> batches
+    CUDA_TRY(launch_ex(a.pdl, a.k.den_slots ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, a.stream, a.k));
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+// (E, CTAs/SM) of the tuned kernels, profiles/r01_sweep_orders.txt and r02 sweeps.  Even-odd contractions from order 3
+// up, plain contractions below; the affine fast path always uses the even-odd kernel.
+template <bool AFF, bool DET>
+int launch_default(LpfApplyArgs &a)
+{
+    if constexpr (AFF) {
+        if constexpr (P == 1) return launch_persistent<16, 4, true, true>(a);
+        else if constexpr (P == 2) return launch_persistent<8, 4, true, true>(a);
+        else if constexpr (P == 3) return launch_persistent<8, 2, true, true>(a);
+        else if constexpr (P == 4) return launch_persistent<3, 4, true, true>(a);
+        else if constexpr (P == 5) return launch_persistent<3, 2, true, true>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 3, true, true>(a);
+        else return launch_persistent<1, 2, true, true>(a);
+    } else {
+        if constexpr (P == 1) return launch_persistent<16, 3, false, false, DET>(a);
+        else if constexpr (P == 2) return launch_persistent<8, 3, false, false, DET>(a);
+        else if constexpr (P == 3) return launch_persistent<8, 2, true, false, DET>(a);
+        else if constexpr (P == 4) return launch_persistent<3, 3, true, false, DET>(a);
+        else if constexpr (P == 5) return launch_persistent<3, 2, true, false, DET>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 2, true, false, DET>(a);
+        else if constexpr (P <= 8) return launch_persistent<1, 2, true, false, DET>(a);
+        else return launch_persistent<1, 1, true, false, DET>(a);
+    }
+}
+
+}  // namespace
+
+int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
+{
+    const int v = a.variant;
+    if (a.k.yE != nullptr) return launch_default<false, true>(a);       // deterministic: E-vector output
+    if (a.affine) return launch_default<true, false>(a);
+    if (v == 0) return launch_default<false, false>(a);
+    if (v == 20) {          // plain contractions on the TMA pipeline
+        if constexpr (P == 1) return launch_persistent<16, 3, false>(a);
+        else if constexpr (P == 2) return launch_persistent<8, 3, false>(a);
+        else if constexpr (P == 3) return launch_persistent<5, 3, false>(a);
+        else if constexpr (P == 4) return launch_persistent<3, 3, false>(a);
+        else if constexpr (P == 5) return launch_persistent<2, 3, false>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 2, false>(a);
+        else if constexpr (P <= 8) return launch_persistent<2, 1, false>(a);
+        else return launch_persistent<1, 1, false>(a);
+    }
+    if (v >= 30 && v < 40) {      // even-odd contractions, alternative (E, CTAs/SM) pairs for the tuning sweep
+        if constexpr (P == 1) { if (v == 31) return launch_persistent<32, 2, true>(a); return launch_persistent<16, 3, true>(a); }
+        else if constexpr (P == 2) { if (v == 31) return launch_persistent<16, 2, true>(a); return launch_persistent<8, 3, true>(a); }
+        else if constexpr (P == 3) { if (v == 31) return launch_persistent<5, 4, true>(a); return launch_persistent<5, 3, true>(a); }
+        else if constexpr (P == 4) { if (v == 31) return launch_persistent<4, 3, true>(a); if (v == 32) return launch_persistent<2, 5, true>(a); return launch_persistent<3, 4, true>(a); }
+        else if constexpr (P == 5) { if (v == 31) return launch_persistent<2, 4, true>(a); return launch_persistent<2, 3, true>(a); }
+        else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); return launch_persistent<2, 3, true>(a); }
+        else if constexpr (P == 7) { if (v == 31) return launch_persistent<2, 2, true>(a); if (v == 32) return launch_persistent<1, 3, true>(a); return launch_persistent<2, 1, true>(a); }
+        else if constexpr (P == 8) { if (v == 31) return launch_persistent<2, 1, true>(a); return launch_persistent<1, 2, true>(a); }
+        else return launch_default<false, false>(a);
+    }
+    lpf::set_error("unknown apply_variant " + std::to_string(v));
+    return LPF_ERR_ARG;
+}
+
+int LPF_CAT(lpf_apply_E_p, LPF_ORDER)(const double *qd, const double *xE, double *yE, int ne, cudaStream_t stream)
+{
+    constexpr int E = P == 1 ? 16 : P == 2 ? 16 : P == 3 ? 8 : P <= 5 ? 4 : P == 6 ? 4 : P <= 8 ? 2 : 1;
+    constexpr bool PF = P <= 5;
+    using C = ApplyCfg<P, E>;
+    auto kern = pa_apply_evec_kernel<P, E, PF>;
+    static bool attr_set[16] = {false};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!attr_set[dev & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        attr_set[dev & 15] = true;
+    }
+    const int grid = (ne + E - 1) / E;
+    if (grid == 0) return LPF_OK;
+    kern<<<grid, C::NT, C::SMEM_BYTES, stream>>>(qd, xE, yE, ne);
+    CUDA_TRY(cudaGetLastError());
+    return LPF_OK;
+}
+
+// B, G: [Q][D] row-major; builds the interleaved {B, G} table and the even / odd half tables (pa_apply_eo.cuh) and uploads
+// them to the CURRENT device
+int LPF_CAT(lpf_apply_tables_p, LPF_ORDER)(const double *B, const double *G, const double *qwts)
+{
+    constexpr int D = P + 1, Q = P + 2, DC = (D + 1) / 2, DH = D / 2, QC = (Q + 1) / 2, QH = Q / 2;
+    std::vector<LpfOrderTab<P>> tabs(2);
+    LpfOrderTab<P> &t = tabs[0];
+    std::memset(&t, 0, sizeof(t));
+    auto Bm = [&](int q, int d) { return B[(size_t)q * D + d]; };
+    auto Gm = [&](int q, int d) { return G[(size_t)q * D + d]; };
+    for (int i = 0; i < Q * D; i++) { t.BG[2 * i] = B[i]; t.BG[2 * i + 1] = G[i]; }
+    for (int q = 0; q < Q; q++) t.qwts[q] = qwts[q];
+    for (int q = 0; q < QC; q++) {
+        for (int d = 0; d < DC; d++) {
+            t.BeF[q * DC + d] = d < DH ? 0.5 * (Bm(q, d) + Bm(q, D - 1 - d)) : Bm(q, d);
+            t.GeF[q * DC + d] = d < DH ? 0.5 * (Gm(q, d) + Gm(q, D - 1 - d)) : Gm(q, d);
+        }
+        for (int d = 0; d < DH; d++) {
+            t.BoF[q * DH + d] = 0.5 * (Bm(q, d) - Bm(q, D - 1 - d));
+            t.GoF[q * DH + d] = 0.5 * (Gm(q, d) - Gm(q, D - 1 - d));
+        }
+    }
+    for (int d = 0; d < DC; d++) {
+        for (int q = 0; q < QC; q++) {
+            t.BeT[d * QC + q] = q < QH ? 0.5 * (Bm(q, d) + Bm(Q - 1 - q, d)) : Bm(q, d);
+            t.GeT[d * QC + q] = q < QH ? 0.5 * (Gm(q, d) + Gm(Q - 1 - q, d)) : Gm(q, d);
+        }
+        for (int q = 0; q < QH; q++) {
+            t.BoT[d * QH + q] = 0.5 * (Bm(q, d) - Bm(Q - 1 - q, d));
+            t.GoT[d * QH + q] = 0.5 * (Gm(q, d) - Gm(Q - 1 - q, d));
+        }
+    }
+    tabs[1] = tabs[0];
+    CUDA_TRY(cudaMemcpyToSymbol(c_ot, tabs.data(), 2 * sizeof(LpfOrderTab<P>)));
+    return LPF_OK;
+}

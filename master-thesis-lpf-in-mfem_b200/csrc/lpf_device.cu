@@ -12,29 +12,12 @@
 #include "../../include/lpf_b200.h"
 #include "../host/lpf_common.hpp"
 #include "../host/lpf_host.hpp"
+#include "apply_api.hpp"
+#include "dev_util.cuh"
 #include "lpf_comm.hpp"
 #include "pa_kernels.cuh"
-#include "pa_apply_pipe.cuh"
-#include "pa_apply_tma.cuh"
-#include "pa_apply_eo.cuh"
 #include "vec_kernels.cuh"
 #include "p2p.cuh"
-
-#define CUDA_TRY(call)                                                                              \
-    do {                                                                                            \
-        cudaError_t err__ = (call);                                                                 \
-        if (err__ != cudaSuccess) {                                                                 \
-            lpf::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" __FILE__ ":" + \
-                           std::to_string(__LINE__) + ")");                                         \
-            return LPF_ERR_CUDA;                                                                    \
-        }                                                                                           \
-    } while (0)
-
-#define LPF_TRY(call)                    \
-    do {                                 \
-        int rc__ = (call);               \
-        if (rc__ != LPF_OK) return rc__; \
-    } while (0)
 
 namespace {
 
@@ -48,19 +31,6 @@ int upload(T *&dst, const T *src, size_t n, size_t *bytes)
     else CUDA_TRY(cudaMemset(dst, 0, n * sizeof(T)));
     if (bytes) *bytes += n * sizeof(T);
     return LPF_OK;
-}
-
-// Kernel launch with (optionally) the programmatic-dependent-launch attribute; see griddep_wait() in vec_kernels.cuh.
-template <class... KArgs, class... Args>
-cudaError_t launch_ex(bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
 inline int vec_grid(int n, int sm_count)
@@ -89,6 +59,13 @@ struct lpf_ctx {
     int pdl = 1;              // programmatic dependent launch between the kernels of a PCG iteration
     bool pdl_now = false;     // set while pcg_iteration() enqueues
     int max_ctas = 0;
+    int verbose = 0;
+    std::vector<std::pair<std::string, long>> env_opts;   // LPF_DEBUG_ENV builds only
+    // deterministic mode (option "deterministic"): the restriction-transpose is an ordered gather of an E-vector instead
+    // of red.global.add, the diagonal likewise -- bit-identical results (and CG iteration counts) from run to run
+    int deterministic = 0;
+    double *yE = nullptr;
+    int *det_off = nullptr, *det_idx = nullptr;
     int ess_general = 0;      // lpf_pcg: search directions may be non-zero on essential dofs
     // geometry / maps
     double *corners = nullptr, *jac = nullptr, *jinv_z = nullptr, *qd = nullptr;
@@ -134,9 +111,12 @@ struct lpf_ctx {
     P2PDev p2p{};
     P2PTail tail{};           // set around PCG applies when the exchange rides on the apply kernel
     unsigned int *p2p_done = nullptr;
-    int p2p_fuse = 0;         // option: run the halo-sum + (d, A d) all-reduce in the LAST CTA of the apply kernel instead of
-                              // the separate multi-CTA LL kernel (measured slower: 32 vs 21 us per iteration at 2 x 150k dofs)
-    int p2p_fuse_max = 2048;  // ... while the interface has at most this many entries (one CTA runs the tail)
+    int p2p_fuse = 2;         // option: how the halo-sum + (d, A d) all-reduce of a PCG apply run (p2p_types.hpp, P2PTail):
+                              // 0 = separate multi-CTA LL kernel after the apply; 1 = in the LAST CTA of the apply kernel
+                              // (measured slower: 32 vs 21 us per iteration at 2 x 150k dofs); 2 = inside the apply kernel,
+                              // overlapped with the interior elements
+    int p2p_fuse_max = 2048;  // mode 1 only: while the interface has at most this many entries (one CTA runs the tail)
+    int n_if_elems = 0;       // elements [0, n_if_elems) cover every element that touches a dof shared with another rank
     // host staging for *_host entry points
     double *hx = nullptr, *hy = nullptr;
     // pipelined host entry point (lpf_apply_T_host): element chunks / dof ranges, copy streams, events
@@ -157,181 +137,74 @@ struct lpf_ctx {
 };
 
 // ------------------------------------------------------------------------------------------------
-// apply kernel dispatch
+// apply kernel dispatch (kernels: one translation unit per order, apply_api.hpp)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-template <int P, int E, bool PF, bool EVEC, int MINB>
-int apply_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
+// Persistent L-vector apply y (+)= G^T A_E G x on the elements [sub_e0, sub_e0 + sub_ne) (default: all).  With yE != nullptr
+// (deterministic mode) the kernel writes the E-vector instead of scatter-adding and the caller assembles y.
+int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status, double *yE = nullptr)
 {
-    using C = ApplyCfg<P, E>;
-    auto kern = pa_apply_kernel<P, E, PF, EVEC, MINB>;
-    static bool attr_set[16] = {false};
-    if (!attr_set[c->dev & 15]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        attr_set[c->dev & 15] = true;
-    }
-    const int grid = (c->ne + E - 1) / E;
-    if (grid == 0) return LPF_OK;
-    kern<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return LPF_OK;
-}
-
-template <int P, int E, int MINB>
-int apply_pipe_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
-{
-    using C = ApplyCfg<P, E>;
-    static int blocks_per_sm[16] = {0};
-    auto kd = pa_apply_pipe_kernel<P, E, true, MINB>;
-    auto kn = pa_apply_pipe_kernel<P, E, false, MINB>;
-    int &bps = blocks_per_sm[c->dev & 15];
-    if (bps == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
-        if (bps < 1) bps = 1;
-    }
-    const int nb = (c->ne + E - 1) / E;
-    if (nb == 0) return LPF_OK;
-    const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
-    if (den) kd<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
-    else kn<<<grid, C::NT, C::SMEM_BYTES, c->stream>>>(c->qd, gmap, x, y, c->ne, den, status);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    return LPF_OK;
-}
-
-template <int P, int E, int MINB, bool EO = false, bool AFF = false>
-int apply_tma_launch_t(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
-{
-    using C = TmaCfg<P, E, AFF>;
-    static int blocks_per_sm[16] = {0};
-    auto kd = EO ? pa_apply_eo_kernel<P, E, true, MINB, AFF> : pa_apply_tma_kernel<P, E, true, MINB>;
-    auto kn = EO ? pa_apply_eo_kernel<P, E, false, MINB, AFF> : pa_apply_tma_kernel<P, E, false, MINB>;
-    int &bps = blocks_per_sm[c->dev & 15];
-    if (bps == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
-        if (bps < 1) bps = 1;
-        if (std::getenv("LPF_VERBOSE")) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, C::NT, (size_t)C::SMEM_BYTES, bps);
-    }
-    // optional element sub-range [sub_e0, sub_e0 + sub_ne): one element's data is contiguous, so a sub-range is a pointer offset
+    const int D3 = c->D * c->D * c->D, DP3 = (D3 + 3) & ~3, QE = 6 * c->Q * c->Q * c->Q;
+    // optional element sub-range: one element's data is contiguous, so a sub-range is a pointer offset
     const int e0 = c->sub_ne >= 0 ? c->sub_e0 : 0, ne = c->sub_ne >= 0 ? c->sub_ne : c->ne;
-    const int nb = (ne + E - 1) / E;
-    if (nb == 0) return LPF_OK;
-    const int grid = std::min(nb, c->max_ctas > 0 ? c->max_ctas : bps * c->sm_count);
-    const double *qsrc = AFF ? c->qa + (size_t)e0 * 6 : c->qd + (size_t)e0 * C::QE;
-    CUDA_TRY(launch_ex(c->pdl_now, den ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, c->stream, qsrc, gmap + (size_t)e0 * C::DP3, x, y, ne, den, status, c->tail));
+    LpfApplyArgs a;
+    a.dev = c->dev; a.sm_count = c->sm_count; a.stream = c->stream; a.variant = c->variant; a.max_ctas = c->max_ctas;
+    a.pdl = c->pdl_now; a.verbose = c->verbose != 0;
+    a.affine = yE == nullptr && c->variant == 0 && c->affine && c->affine_ok;
+    a.k.qd = a.affine ? c->qa + (size_t)e0 * 6 : c->qd + (size_t)e0 * QE;
+    a.k.gmap = gmap + (size_t)e0 * DP3;
+    a.k.x = x; a.k.y = y; a.k.yE = yE ? yE + (size_t)e0 * D3 : nullptr; a.k.ne = ne;
+    a.k.den_slots = den; a.k.status = status; a.k.tail = c->tail;
+    int rc = LPF_ERR_UNSUPPORTED;
+#define LPF_CALL(P) rc = lpf_apply_L_p##P(a)
+    LPF_ORDER_SWITCH(c->p, LPF_CALL, lpf::set_error("unsupported order"))
+#undef LPF_CALL
+    if (rc == LPF_OK && a.grid > 0) c->launches++;
+    return rc;
+}
+
+// deterministic restriction-transpose of the E-vector c->yE into y (rows with skip != 0 stay 0)
+int det_gather(lpf_ctx *c, const uint8_t *skip, double *y)
+{
+    det_gather_kernel<<<(c->ndof + 255) / 256, 256, 0, c->stream>>>(c->ndof, c->det_off, c->det_idx, c->yE, skip, y);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
 }
 
-// Kernel selection.  L-vector applies (the hot path) use the persistent TMA-staged kernel; variant 0 is the
-// tuned default per order, variants 1..3 are alternative (elements per CTA, CTAs per SM) pairs kept for the
-// tuning sweep in bench.py, variants >= 100 select the earlier one-batch-per-CTA kernel (100 + E index) and
-// 200+ the register-pipelined one, so every design that profiles/ discusses stays measurable.
-// E-vector applies (AddMultPA adapter entry point) use the one-batch-per-CTA kernel.
-#define LPF_TMA(P, E, MINB) return apply_tma_launch_t<P, E, MINB>(c, gmap, x, y, den, status)
-#define LPF_EO(P, E, MINB) return apply_tma_launch_t<P, E, MINB, true>(c, gmap, x, y, den, status)
-#define LPF_EOA(P, E, MINB) return apply_tma_launch_t<P, E, MINB, true, true>(c, gmap, x, y, den, status)
-#define LPF_OLD(P, E, PF) return apply_launch_t<P, E, PF, EVEC, 1>(c, gmap, x, y, den, status)
-template <bool EVEC>
-int apply_launch(lpf_ctx *c, const int *gmap, const double *x, double *y, double *den, const int *status)
+// y = G^T A_E G x on this rank's elements: scatter-add into the zeroed y, or (deterministic) E-vector + ordered gather.
+// `constrained`: essential rows / columns masked (gmap_c).  zero_y: y is not known to be zero yet.
+int apply_full(lpf_ctx *c, bool constrained, const double *x, double *y, double *den, const int *status, bool zero_y)
 {
-    int v = c->variant;
-    const bool plain = (v == 20);
-    if (plain) v = -1;            // falls through to the default (E, MINB) of the plain-contraction TMA kernel
-    if (EVEC || v >= 100) {
-        switch (c->p) {
-            case 1: LPF_OLD(1, 16, true);
-            case 2: LPF_OLD(2, 16, true);
-            case 3: if (v == 101) LPF_OLD(3, 4, true); LPF_OLD(3, 8, true);
-            case 4:
-                if (v == 101) LPF_OLD(4, 8, true);
-                if (v == 102) LPF_OLD(4, 4, false);
-                if (v == 103) LPF_OLD(4, 2, true);
-                if (v == 104) LPF_OLD(4, 3, true);
-                LPF_OLD(4, 4, true);
-            case 5: if (v == 101) LPF_OLD(5, 2, true); LPF_OLD(5, 4, true);
-            case 6: if (v == 101) LPF_OLD(6, 2, true); LPF_OLD(6, 4, false);
-            case 7: LPF_OLD(7, 2, false);
-            case 8: LPF_OLD(8, 2, false);
-            default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
-        }
+    const int *gm = constrained ? c->gmap_c : c->gmap;
+    if (c->deterministic) {
+        LPF_TRY(apply_launch(c, gm, x, y, den, status, c->yE));
+        return det_gather(c, constrained ? c->essmask : nullptr, y);
     }
-    if constexpr (!EVEC) {
-        if (v == 0 && c->affine && c->affine_ok) {      // affine fast path: no q-data stream (pa_apply_eo.cuh)
-            switch (c->p) {
-                case 1: LPF_EOA(1, 16, 4);
-                case 2: LPF_EOA(2, 8, 4);
-                case 3: LPF_EOA(3, 8, 2);
-                case 4: LPF_EOA(4, 3, 4);
-                case 5: LPF_EOA(5, 3, 2);
-                case 6: LPF_EOA(6, 2, 3);
-                case 7: LPF_EOA(7, 1, 2);
-                case 8: LPF_EOA(8, 1, 2);
-                default: break;
-            }
-        }
-        if (v == 0) {                 // tuned defaults (profiles/r01_sweep_orders.txt): even-odd kernel from order 3 up
-            switch (c->p) {
-                case 3: LPF_EO(3, 8, 2);
-                case 4: LPF_EO(4, 3, 3);
-                case 5: LPF_EO(5, 3, 2);
-                case 6: LPF_EO(6, 2, 2);
-                case 7: LPF_EO(7, 1, 2);
-                case 8: LPF_EO(8, 1, 2);
-                default: break;       // orders 1, 2: plain contractions below
-            }
-        }
-        if (v >= 30 && v < 40) {      // even-odd contractions (pa_apply_eo.cuh)
-            switch (c->p) {
-                case 1: if (v == 31) LPF_EO(1, 32, 2); LPF_EO(1, 16, 3);
-                case 2: if (v == 31) LPF_EO(2, 16, 2); LPF_EO(2, 8, 3);
-                case 3: if (v == 31) LPF_EO(3, 8, 2); if (v == 33) LPF_EO(3, 7, 3); if (v == 34) LPF_EO(3, 5, 4); LPF_EO(3, 5, 3);
-                case 4: if (v == 31) LPF_EO(4, 4, 3); if (v == 32) LPF_EO(4, 2, 5); if (v == 33) LPF_EO(4, 3, 4); LPF_EO(4, 3, 3);
-                case 5: if (v == 31) LPF_EO(5, 3, 2); if (v == 32) LPF_EO(5, 2, 4); LPF_EO(5, 2, 3);
-                case 6: if (v == 31) LPF_EO(6, 3, 1); if (v == 32) LPF_EO(6, 2, 3); LPF_EO(6, 2, 2);
-                case 7: if (v == 31) LPF_EO(7, 1, 2); if (v == 32) LPF_EO(7, 2, 2); LPF_EO(7, 2, 1);
-                case 8: if (v == 31) LPF_EO(8, 1, 2); LPF_EO(8, 2, 1);
-                default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
-            }
-        }
-        switch (c->p) {
-            case 1: if (v == 1) LPF_TMA(1, 8, 4); if (v == 2) LPF_TMA(1, 32, 2); LPF_TMA(1, 16, 3);
-            case 2: if (v == 1) LPF_TMA(2, 4, 5); if (v == 2) LPF_TMA(2, 16, 2); LPF_TMA(2, 8, 3);
-            case 3: if (v == 1) LPF_TMA(3, 3, 5); if (v == 2) LPF_TMA(3, 8, 2); LPF_TMA(3, 5, 3);
-            case 4:
-                if (v == 1) LPF_TMA(4, 2, 5);
-                if (v == 2) LPF_TMA(4, 4, 3);
-                if (v == 3) LPF_TMA(4, 8, 1);
-                if (v == 4) LPF_TMA(4, 4, 2);
-                if (v == 5) LPF_TMA(4, 2, 4);
-                if (v >= 10 && v < 20) {
-                    if (v == 10) return apply_pipe_launch_t<4, 2, 4>(c, gmap, x, y, den, status);
-                    if (v == 12) return apply_pipe_launch_t<4, 4, 2>(c, gmap, x, y, den, status);
-                    if (v == 14) return apply_pipe_launch_t<4, 3, 3>(c, gmap, x, y, den, status);
-                    return apply_pipe_launch_t<4, 8, 1>(c, gmap, x, y, den, status);
-                }
-                LPF_TMA(4, 3, 3);
-            case 5: if (v == 1) LPF_TMA(5, 3, 2); if (v == 2) LPF_TMA(5, 1, 4); LPF_TMA(5, 2, 3);
-            case 6: if (v == 1) LPF_TMA(6, 1, 3); if (v == 2) LPF_TMA(6, 3, 1); LPF_TMA(6, 2, 2);
-            case 7: if (v == 1) LPF_TMA(7, 1, 2); LPF_TMA(7, 2, 1);
-            case 8: if (v == 1) LPF_TMA(8, 1, 2); LPF_TMA(8, 2, 1);
-            default: lpf::set_error("unsupported order"); return LPF_ERR_UNSUPPORTED;
-        }
-    }
-    return LPF_ERR_UNSUPPORTED;
+    if (zero_y) CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
+    return apply_launch(c, gm, x, y, den, status);
 }
-#undef LPF_TMA
-#undef LPF_EO
-#undef LPF_EOA
-#undef LPF_OLD
 
+// How the halo-sum of an apply runs on this rank (P2PTail::mode): 0 = separate kernel(s) after the element kernel,
+// 1 = in the last CTA of the element kernel, 2 = inside the element kernel, overlapped with the interior elements.
+int tail_mode(const lpf_ctx *c)
+{
+    if (c->nranks == 1 || !c->p2p_on || c->ess_general || c->deterministic || c->halo.n_nbr > 32) return 0;
+    if (c->p2p_fuse == 1) return (c->halo.n_nbr > 0 && c->halo.total <= c->p2p_fuse_max) ? 1 : 0;
+    return c->p2p_fuse == 2 ? 2 : 0;
+}
+
+// constrained apply with the halo-sum (and, inside the PCG, the all-reduce of (d, A d)) riding on the element kernel
+int apply_with_tail(lpf_ctx *c, const double *x, double *y, bool pcg)
+{
+    c->tail.mode = tail_mode(c); c->tail.with_den = pcg ? 1 : 0; c->tail.n_if_batches = c->n_if_elems;
+    c->tail.d = c->p2p; c->tail.h = c->p2p_plan[0];
+    c->tail.st = pcg ? c->st : nullptr; c->tail.den_slots = c->den_slots; c->tail.done = c->p2p_done;
+    const int rc = apply_launch(c, c->gmap_c, x, y, pcg ? c->den_slots : nullptr, pcg ? &c->st->status : nullptr);
+    c->tail.mode = 0;
+    return rc;
+}
 
 int halo_sum(lpf_ctx *c, lpf::HaloPlan &h, double *v)
 {
@@ -501,61 +374,36 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     CUDA_TRY(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (stream) c->stream = (cudaStream_t)stream;
     else { CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
-    if (const char *e = std::getenv("LPF_PDL")) c->pdl = std::atoi(e);          // A/B switches for the drivers
-    if (const char *e = std::getenv("LPF_PCG_CHUNK")) c->chunk = std::max(1, std::atoi(e));
-    if (const char *e = std::getenv("LPF_P2P_FUSE")) c->p2p_fuse = std::atoi(e);
-    if (const char *e = std::getenv("LPF_AFFINE")) c->affine = std::atoi(e);
-    if (const char *e = std::getenv("LPF_APPLY_VARIANT")) c->variant = std::atoi(e);
-    if (const char *e = std::getenv("LPF_MAX_CTAS")) c->max_ctas = std::atoi(e);
-    if (const char *e = std::getenv("LPF_L2_PERSIST")) c->l2_persist = std::atoi(e);
-    if (const char *e = std::getenv("LPF_L2_HINT")) { const int v = std::atoi(e); CUDA_TRY(cudaMemcpyToSymbol(c_l2_stream_hint, &v, sizeof(int))); }
-    if (const char *e = std::getenv("LPF_P2P_FUSE_MAX")) c->p2p_fuse_max = std::atoi(e);
+#ifdef LPF_DEBUG_ENV      // developer builds only: environment overrides of the options (the product reads no environment)
+    for (const char *name : {"pdl", "pcg_chunk", "p2p_fuse", "p2p_fuse_max", "affine", "apply_variant", "max_ctas", "l2_persist", "deterministic", "verbose"}) {
+        std::string env = "LPF_";
+        for (const char *q = name; *q; q++) env += (char)std::toupper(*q);
+        if (const char *e = std::getenv(env.c_str())) c->env_opts.emplace_back(name, std::atol(e));
+    }
+#endif
     c->p = d->order; c->D = d->order + 1; c->Q = d->order + 2;
     c->ne = d->ne; c->ndof = d->ndof; c->ness = d->n_ess; c->nsurf = d->n_surf;
     c->nranks = d->nranks > 0 ? d->nranks : 1; c->rank = d->rank;
     c->n_true_global = d->n_true_global ? d->n_true_global : d->ndof;
     const int D3 = c->D * c->D * c->D, Q3 = c->Q * c->Q * c->Q;
 
-    // basis tables -> constant memory (slot p)
+    // basis tables -> constant memory: slot p of the generic kernels' table, and the apply kernels' own per-order tables
     {
         lpf::Basis1D bs(c->p);
         LpfBasisTab t;
         std::memset(&t, 0, sizeof(t));
         std::copy(bs.B.begin(), bs.B.end(), t.B);
-        for (size_t i = 0; i < bs.B.size(); i++) { t.BG[2 * i] = bs.B[i]; t.BG[2 * i + 1] = bs.G[i]; }
         std::copy(bs.G.begin(), bs.G.end(), t.G);
         std::copy(bs.Dhat.begin(), bs.Dhat.end(), t.Dhat);
         std::copy(bs.nodes.begin(), bs.nodes.end(), t.nodes);
         std::copy(bs.qpts.begin(), bs.qpts.end(), t.qpts);
         std::copy(bs.qwts.begin(), bs.qwts.end(), t.qwts);
         CUDA_TRY(cudaMemcpyToSymbol(c_tab, &t, sizeof(t), sizeof(LpfBasisTab) * c->p));
-        // even / odd half tables of the (anti)symmetric B and G (pa_apply_eo.cuh)
-        LpfEoTab eo;
-        std::memset(&eo, 0, sizeof(eo));
-        const int D = bs.D, Q = bs.Q, DC = (D + 1) / 2, DH = D / 2, QC = (Q + 1) / 2, QH = Q / 2;
-        auto Bm = [&](int q, int d) { return bs.B[(size_t)q * D + d]; };
-        auto Gm = [&](int q, int d) { return bs.G[(size_t)q * D + d]; };
-        for (int q = 0; q < QC; q++) {
-            for (int d = 0; d < DC; d++) {
-                eo.BeF[q * DC + d] = d < DH ? 0.5 * (Bm(q, d) + Bm(q, D - 1 - d)) : Bm(q, d);
-                eo.GeF[q * DC + d] = d < DH ? 0.5 * (Gm(q, d) + Gm(q, D - 1 - d)) : Gm(q, d);
-            }
-            for (int d = 0; d < DH; d++) {
-                eo.BoF[q * DH + d] = 0.5 * (Bm(q, d) - Bm(q, D - 1 - d));
-                eo.GoF[q * DH + d] = 0.5 * (Gm(q, d) - Gm(q, D - 1 - d));
-            }
-        }
-        for (int d = 0; d < DC; d++) {
-            for (int q = 0; q < QC; q++) {
-                eo.BeT[d * QC + q] = q < QH ? 0.5 * (Bm(q, d) + Bm(Q - 1 - q, d)) : Bm(q, d);
-                eo.GeT[d * QC + q] = q < QH ? 0.5 * (Gm(q, d) + Gm(Q - 1 - q, d)) : Gm(q, d);
-            }
-            for (int q = 0; q < QH; q++) {
-                eo.BoT[d * QH + q] = 0.5 * (Bm(q, d) - Bm(Q - 1 - q, d));
-                eo.GoT[d * QH + q] = 0.5 * (Gm(q, d) - Gm(Q - 1 - q, d));
-            }
-        }
-        CUDA_TRY(cudaMemcpyToSymbol(c_eo, &eo, sizeof(eo), sizeof(LpfEoTab) * c->p));
+        int rc = LPF_ERR_UNSUPPORTED;
+#define LPF_CALL(P) rc = lpf_apply_tables_p##P(bs.B.data(), bs.G.data(), bs.qwts.data())
+        LPF_ORDER_SWITCH(c->p, LPF_CALL, lpf::set_error("unsupported order"))
+#undef LPF_CALL
+        LPF_TRY(rc);
     }
     if (d->corners) LPF_TRY(upload(c->corners, d->corners, (size_t)c->ne * 24, &c->bytes));
     if (d->jac) LPF_TRY(upload(c->jac, d->jac, (size_t)c->ne * Q3 * 9, &c->bytes));
@@ -641,6 +489,13 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         LPF_TRY(upload_halo(c->shalo, d->s_n_nbr, d->s_nbr_rank, d->s_nbr_offset, d->s_send, d->s_n_shared, d->s_shared,
                             d->s_red_off, d->s_red_src, &c->bytes));
         if (c->nranks <= LPF_P2P_MAXR) LPF_TRY(p2p_create(c));
+        // how far the elements touching shared dofs reach in the element order (lpf_space_create puts them first): the
+        // overlapped halo exchange sends the interface as soon as these are done
+        std::vector<uint8_t> sh((size_t)c->ndof, 0);
+        for (int i = 0; i < d->n_shared; i++) sh[d->shared_dofs[i]] = 1;
+        c->n_if_elems = 0;
+        for (int e = 0; e < c->ne; e++)
+            for (int k = 0; k < D3; k++) if (sh[d->gather[(size_t)e * D3 + k]]) { c->n_if_elems = e + 1; break; }
     }
     // surface tables
     if (c->nsurf > 0) {
@@ -686,6 +541,27 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     return LPF_OK;
 }
 
+// Deterministic mode: transposed element map (offsets / indices of ElementRestriction, indices ascending per dof) and
+// the E-vector the apply kernel writes instead of scatter-adding.  Built on first use from the device copy of the map.
+int det_setup(lpf_ctx *c)
+{
+    if (c->det_off) return LPF_OK;
+    CUDA_TRY(cudaSetDevice(c->dev));
+    const int D3 = c->D * c->D * c->D, DP3 = (D3 + 3) & ~3;
+    std::vector<int> gm((size_t)c->ne * DP3);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (!gm.empty()) CUDA_TRY(cudaMemcpy(gm.data(), c->gmap, gm.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<int> off((size_t)c->ndof + 1, 0), idx((size_t)c->ne * D3);
+    for (int e = 0; e < c->ne; e++) for (int k = 0; k < D3; k++) off[gm[(size_t)e * DP3 + k] + 1]++;
+    for (int i = 0; i < c->ndof; i++) off[i + 1] += off[i];
+    std::vector<int> pos(off.begin(), off.end() - 1);
+    for (int e = 0; e < c->ne; e++) for (int k = 0; k < D3; k++) idx[pos[gm[(size_t)e * DP3 + k]]++] = e * D3 + k;
+    LPF_TRY(upload(c->det_off, off.data(), off.size(), &c->bytes));
+    LPF_TRY(upload(c->det_idx, idx.data(), idx.size(), &c->bytes));
+    LPF_TRY(upload(c->yE, (const double *)nullptr, (size_t)c->ne * D3, &c->bytes));
+    return LPF_OK;
+}
+
 void free_halo(lpf::HaloPlan &h)
 {
     cudaFree(h.send_dofs); cudaFree(h.shared); cudaFree(h.red_off); cudaFree(h.red_src); cudaFree(h.sendbuf); cudaFree(h.recvbuf);
@@ -701,10 +577,11 @@ lpf_ctx *lpf_create(const lpf_space_desc *desc, int device, void *stream)
         lpf::set_error("lpf_create: incomplete descriptor");
         return nullptr;
     }
-    if (desc->order < 1 || desc->order > LPF_MAXP) { lpf::set_error("lpf_create: order must be in 1..8"); return nullptr; }
+    if (desc->order < 1 || desc->order > LPF_MAXP) { lpf::set_error("lpf_create: order must be in 1..10"); return nullptr; }
     if (desc->n_ess > 0 && !desc->ess) { lpf::set_error("lpf_create: n_ess > 0 but ess == NULL"); return nullptr; }
     auto *c = new lpf_ctx;
     if (create_impl(c, desc, device, stream) != LPF_OK) { lpf_destroy(c); return nullptr; }
+    for (auto &o : c->env_opts) if (lpf_set_option(c, o.first.c_str(), o.second) != LPF_OK) { lpf_destroy(c); return nullptr; }
     return c;
 }
 
@@ -718,7 +595,7 @@ void lpf_destroy(lpf_ctx *c)
     c->comm.destroy();
     void *ptrs[] = {c->qa, c->corners, c->jac, c->jinv_z, c->qd, c->gmap, c->gmap_c, c->ess, c->essmask, c->owned, c->surf_owned, c->dinv, c->r,
                     c->zdad, c->X, c->Bv, c->tmp, c->den_slots, c->partials, c->st, c->bad, c->surf2vol,
-                    c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->cabsy, c->env, c->wsum, c->rk_k,
+                    c->yE, c->det_off, c->det_idx, c->surf_mult, c->sd_off, c->sd_elem, c->sd_node, c->surf_xy, c->cgen, c->cabs, c->cabsy, c->env, c->wsum, c->rk_k,
                     c->rk_y, c->rk_z, c->state_dev};
     for (void *p : ptrs) if (p) cudaFree(p);
     free_halo(c->halo); free_halo(c->shalo);
@@ -768,7 +645,8 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "affine") c->affine = (int)value;
     else if (k == "host_pipeline") c->host_pipeline = (int)value;
     else if (k == "l2_persist") c->l2_persist = (int)value;
-    else if (k == "l2_hint") { const int v = (int)value; CUDA_TRY(cudaMemcpyToSymbol(c_l2_stream_hint, &v, sizeof(int))); }
+    else if (k == "verbose") c->verbose = (int)value;
+    else if (k == "deterministic") { if (value) LPF_TRY(det_setup(c)); c->deterministic = value ? 1 : 0; }
     else if (k == "p2p_fuse_max") c->p2p_fuse_max = (int)value;
     else if (k == "max_ctas") c->max_ctas = (int)value;      // persistent kernels: cap the grid (tests force many batches per CTA)
     else { lpf::set_error("lpf_set_option: unknown option " + k); return LPF_ERR_ARG; }
@@ -857,24 +735,34 @@ int lpf_pa_apply_E(lpf_ctx *c, const double *xE, double *yE)
 {
     if (!c || !xE || !yE) { lpf::set_error("lpf_pa_apply_E: null argument"); return LPF_ERR_ARG; }
     if (!c->setup_done) { lpf::set_error("lpf_pa_apply_E before lpf_pa_setup"); return LPF_ERR_STATE; }
-    return apply_launch<true>(c, nullptr, xE, yE, nullptr, nullptr);
+    CUDA_TRY(cudaSetDevice(c->dev));
+    int rc = LPF_ERR_UNSUPPORTED;
+#define LPF_CALL(P) rc = lpf_apply_E_p##P(c->qd, xE, yE, c->ne, c->stream)
+    LPF_ORDER_SWITCH(c->p, LPF_CALL, lpf::set_error("unsupported order"))
+#undef LPF_CALL
+    if (rc == LPF_OK && c->ne) c->launches++;
+    return rc;
 }
 
 int lpf_apply_L(lpf_ctx *c, const double *x, double *y)
 {
     if (!c || !x || !y) { lpf::set_error("lpf_apply_L: null argument"); return LPF_ERR_ARG; }
     if (!c->setup_done) { lpf::set_error("lpf_apply_L before lpf_pa_setup"); return LPF_ERR_STATE; }
-    CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
-    return apply_launch<false>(c, c->gmap, x, y, nullptr, nullptr);
+    return apply_full(c, false, x, y, nullptr, nullptr, true);
 }
 
 int lpf_apply_T(lpf_ctx *c, const double *x, double *y)
 {
     if (!c || !x || !y) { lpf::set_error("lpf_apply_T: null argument"); return LPF_ERR_ARG; }
     if (!c->setup_done) { lpf::set_error("lpf_apply_T before lpf_pa_setup"); return LPF_ERR_STATE; }
-    CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
-    LPF_TRY(apply_launch<false>(c, c->gmap_c, x, y, nullptr, nullptr));
-    LPF_TRY(halo_sum(c, c->halo, y));
+    if (tail_mode(c) == 2 && c->sub_ne < 0) {
+        // multi-GPU: the halo-sum rides on the element kernel, overlapped with the interior elements (p2p_dev.cuh)
+        CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
+        LPF_TRY(apply_with_tail(c, x, y, false));
+    } else {
+        LPF_TRY(apply_full(c, true, x, y, nullptr, nullptr, true));
+        LPF_TRY(halo_sum(c, c->halo, y));
+    }
     if (c->ness) {
         copy_at_kernel<<<(c->ness + 255) / 256, 256, 0, c->stream>>>(c->ness, c->ess, x, y);
         c->launches++;
@@ -914,7 +802,7 @@ static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
         for (; waited < c->hp_x_ranges_needed[k]; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
         c->sub_e0 = k ? c->hp_elem_end[k - 1] : 0;
         c->sub_ne = c->hp_elem_end[k] - c->sub_e0;
-        rc = apply_launch<false>(c, c->gmap_c, x, y, nullptr, nullptr);
+        rc = apply_launch(c, c->gmap_c, x, y, nullptr, nullptr);
         c->sub_ne = -1;
         if (rc != LPF_OK) break;
         if (c->hp_final[k].empty()) continue;
@@ -967,14 +855,18 @@ int lpf_apply_T_host(lpf_ctx *c, const double *xh, double *yh)
 {
     if (!c || !xh || !yh) { lpf::set_error("lpf_apply_T_host: null argument"); return LPF_ERR_ARG; }
     if (!c->setup_done) { lpf::set_error("lpf_apply_T_host before lpf_pa_setup"); return LPF_ERR_STATE; }
-    const bool tma_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
-    if (c->host_pipeline && !c->hp_elem_end.empty() && tma_kernel) return apply_T_host_pipelined(c, xh, yh);
-    const size_t nb = sizeof(double) * c->ndof;
-    CUDA_TRY(cudaMemcpyAsync(c->X, xh, nb, cudaMemcpyHostToDevice, c->stream));
-    LPF_TRY(lpf_apply_T(c, c->X, c->tmp));
-    CUDA_TRY(cudaMemcpyAsync(yh, c->tmp, nb, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    return LPF_OK;
+    int rc;
+    if (c->host_pipeline && !c->hp_elem_end.empty() && !c->deterministic) rc = apply_T_host_pipelined(c, xh, yh);
+    else {
+        const size_t nb = sizeof(double) * c->ndof;
+        CUDA_TRY(cudaMemcpyAsync(c->X, xh, nb, cudaMemcpyHostToDevice, c->stream));
+        LPF_TRY(lpf_apply_T(c, c->X, c->tmp));
+        CUDA_TRY(cudaMemcpyAsync(yh, c->tmp, nb, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        rc = LPF_OK;
+    }
+    if (rc == LPF_OK && lpf_p2p_error(c) != 0) { lpf::set_error("lpf_apply_T_host: peer-memory exchange timed out (a neighbour rank stalled)"); return LPF_ERR_COMM; }
+    return rc;
 }
 
 // ---- a2 -------------------------------------------------------------------------------------------
@@ -982,14 +874,37 @@ int lpf_diag(lpf_ctx *c, double *diag)
 {
     if (!c || !diag) { lpf::set_error("lpf_diag: null argument"); return LPF_ERR_ARG; }
     if (!c->setup_done) { lpf::set_error("lpf_diag before lpf_pa_setup"); return LPF_ERR_STATE; }
-    CUDA_TRY(cudaMemsetAsync(diag, 0, sizeof(double) * c->ndof, c->stream));
     const size_t n = (size_t)c->ne * c->D * c->D * c->D;
+    if (c->deterministic) {      // E-vector diagonal + ordered gather: the summation order of MFEM's CPU restriction-transpose
+        if (n) {
+            CUDA_TRY(cudaMemsetAsync(c->yE, 0, sizeof(double) * n, c->stream));
+            pa_diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->p, c->ne, c->qd, nullptr, c->yE);
+            c->launches++;
+        }
+        LPF_TRY(det_gather(c, nullptr, diag));
+        return halo_sum(c, c->halo, diag);
+    }
+    CUDA_TRY(cudaMemsetAsync(diag, 0, sizeof(double) * c->ndof, c->stream));
     if (n) {
         pa_diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->p, c->ne, c->qd, c->gmap, diag);
         c->launches++;
         CUDA_TRY(cudaGetLastError());
     }
     return halo_sum(c, c->halo, diag);
+}
+
+/* DiffusionIntegrator::AssembleDiagonalPA(Vector &diag): E-vector diagonal, ACCUMULATED into diagE[ne][D^3] */
+int lpf_pa_diag_E(lpf_ctx *c, double *diagE)
+{
+    if (!c || !diagE) { lpf::set_error("lpf_pa_diag_E: null argument"); return LPF_ERR_ARG; }
+    if (!c->setup_done) { lpf::set_error("lpf_pa_diag_E before lpf_pa_setup"); return LPF_ERR_STATE; }
+    const size_t n = (size_t)c->ne * c->D * c->D * c->D;
+    if (n) {
+        pa_diag_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(c->p, c->ne, c->qd, nullptr, diagE);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LPF_OK;
 }
 
 int lpf_jacobi_setup(lpf_ctx *c)
@@ -1055,25 +970,6 @@ int multi_reduce(lpf_ctx *c, int mode)
     return LPF_OK;
 }
 
-// one CG iteration body: update (+ dot), direction, apply (+ den); all skip themselves once status != 0
-bool p2p_fused(const lpf_ctx *c)
-{
-    const bool tail_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
-    // the tail runs in ONE CTA: worth it only while the interface is small (measured: 2 x 585 dofs at big8 p=4 breaks even
-    // with NCCL, 2 x 8481 dofs is 2x slower than separate multi-CTA pack / unpack kernels)
-    return c->p2p_on && c->p2p_fuse && !c->ess_general && tail_kernel && c->halo.n_nbr > 0 && c->halo.n_nbr <= 32 && c->halo.total <= c->p2p_fuse_max;
-}
-
-// constrained apply whose last CTA also does the halo-sum and the all-reduce of (d, A d)
-int apply_with_tail(lpf_ctx *c, const double *x, double *y)
-{
-    c->tail.enabled = 1; c->tail.with_den = 1; c->tail.d = c->p2p; c->tail.h = c->p2p_plan[0];
-    c->tail.st = c->st; c->tail.den_slots = c->den_slots; c->tail.done = c->p2p_done;
-    const int rc = apply_launch<false>(c, c->gmap_c, x, y, c->den_slots, &c->st->status);
-    c->tail.enabled = 0;
-    return rc;
-}
-
 // LL halo-sum of the PCG apply (+ the (d, A d) all-reduce) in one PDL-chained kernel
 int halo_ll(lpf_ctx *c, bool pdl, double *v, bool with_den)
 {
@@ -1084,21 +980,21 @@ int halo_ll(lpf_ctx *c, bool pdl, double *v, bool with_den)
     return LPF_OK;
 }
 
+// one CG iteration body: update (+ dot), direction, apply (+ den); all skip themselves once status != 0
 int pcg_iteration(lpf_ctx *c)
 {
     const int n = c->ndof, g = vec_grid(n, c->sm_count);
     const bool multi = c->nranks > 1;
     const uint8_t *no_mask = nullptr;
-    const bool tma_kernel = c->variant < 10 || c->variant == 20 || (c->variant >= 30 && c->variant < 40) || (c->p != 4 && c->variant < 100);
-    const bool pdl = c->pdl != 0 && tma_kernel && !c->ess_general;
-    if (p2p_fused(c)) {
+    const bool pdl = c->pdl != 0 && !c->ess_general && !c->deterministic;
+    if (tail_mode(c) != 0) {
         // three launches, as on one GPU: the betanom all-reduce runs in the last block of the update kernel, the
-        // halo-sum and the (d, A d) all-reduce in the last CTA of the apply kernel (peer-memory stores + flags)
+        // halo-sum and the (d, A d) all-reduce inside the apply kernel (peer-memory stores + flags)
         CUDA_TRY(launch_ex(pdl, pcg_update_p2p_kernel, dim3(g), dim3(256), 0, c->stream, n, c->X, c->r, c->z, c->d, c->ad, c->dinv, c->owned, c->st, c->partials, c->p2p));
         CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
         c->launches += 2;
         c->pdl_now = pdl;
-        const int rc = apply_with_tail(c, c->d, c->ad);
+        const int rc = apply_with_tail(c, c->d, c->ad, true);
         c->pdl_now = false;
         return rc;
     }
@@ -1109,7 +1005,7 @@ int pcg_iteration(lpf_ctx *c)
         CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
         c->launches += 2;
         c->pdl_now = pdl;
-        const int rc = apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status);
+        const int rc = apply_full(c, true, c->d, c->ad, c->den_slots, &c->st->status, false);
         c->pdl_now = false;
         LPF_TRY(rc);
         return halo_ll(c, pdl, c->ad, true);
@@ -1120,7 +1016,7 @@ int pcg_iteration(lpf_ctx *c)
         LPF_TRY(multi_reduce(c, P2P_RED_BETA));
         pcg_dir_kernel<<<g, 256, 0, c->stream>>>(n, c->z, c->d, c->ad, c->st, c->den_slots);
         c->launches++;
-        LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+        LPF_TRY(apply_full(c, true, c->d, c->ad, c->den_slots, &c->st->status, false));
     } else {
         // single GPU: update -> direction -> apply chained by programmatic dependent launches (the ess_fix kernel of
         // general right-hand sides has no griddep_wait, so that path keeps plain stream order)
@@ -1128,7 +1024,7 @@ int pcg_iteration(lpf_ctx *c)
         CUDA_TRY(launch_ex(pdl, pcg_dir_kernel, dim3(g), dim3(256), 0, c->stream, n, c->z, c->d, c->ad, c->st, c->den_slots));
         c->launches += 2;
         c->pdl_now = pdl;
-        const int rc = apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status);
+        const int rc = apply_full(c, true, c->d, c->ad, c->den_slots, &c->st->status, false);
         c->pdl_now = false;
         LPF_TRY(rc);
     }
@@ -1141,13 +1037,15 @@ int pcg_iteration(lpf_ctx *c)
     return LPF_OK;
 }
 
+int pcg_graph_key(const lpf_ctx *c) { return c->ess_general + 2 * tail_mode(c) + 8 * c->deterministic; }
+
 int pcg_chunk(lpf_ctx *c)
 {
     if (!c->use_graph) {
         for (int i = 0; i < c->chunk; i++) LPF_TRY(pcg_iteration(c));
         return LPF_OK;
     }
-    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk || c->pcg_graph_general != c->ess_general + 2 * (int)p2p_fused(c)) {
+    if (!c->pcg_graph || c->pcg_graph_chunk != c->chunk || c->pcg_graph_general != pcg_graph_key(c)) {
         if (c->pcg_graph) { cudaGraphExecDestroy(c->pcg_graph); c->pcg_graph = nullptr; }
         cudaGraph_t graph = nullptr;
         const long l0 = c->launches;
@@ -1162,7 +1060,7 @@ int pcg_chunk(lpf_ctx *c)
         CUDA_TRY(cudaGraphInstantiate(&c->pcg_graph, graph, 0));
         cudaGraphDestroy(graph);
         c->pcg_graph_chunk = c->chunk;
-        c->pcg_graph_general = c->ess_general + 2 * (int)p2p_fused(c);
+        c->pcg_graph_general = pcg_graph_key(c);
     }
     CUDA_TRY(cudaGraphLaunch(c->pcg_graph, c->stream));
     c->launches += c->pcg_graph_launches;
@@ -1175,9 +1073,11 @@ int pcg_chunk(lpf_ctx *c)
 // they fit the persisting carve-out (<= 75 % of the 126 MB L2) that traffic never reaches HBM; beyond it a fraction does.
 int pcg_l2_window(lpf_ctx *c, bool on)
 {
-    static int max_persist[16] = {-1}, max_window[16] = {0};
+    static int max_persist[16], max_window[16] = {0};
+    static bool queried[16] = {false};
     int &mp = max_persist[c->dev & 15];
-    if (mp < 0) {
+    if (!queried[c->dev & 15]) {
+        queried[c->dev & 15] = true;
         cudaDeviceProp prop;
         CUDA_TRY(cudaGetDeviceProperties(&prop, c->dev));
         mp = prop.persistingL2CacheMaxSize;
@@ -1226,15 +1126,16 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         c->launches++;
         t = c->tmp;
     }
-    const bool ll_path = multi && c->p2p_on && !c->ess_general && !p2p_fused(c);
-    if (p2p_fused(c)) {
+    const bool fused = tail_mode(c) != 0;
+    const bool ll_path = multi && c->p2p_on && !c->ess_general && !fused;
+    if (fused) {
         pcg_init_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials, c->p2p);
         c->launches++;
-        LPF_TRY(apply_with_tail(c, c->d, c->ad));
+        LPF_TRY(apply_with_tail(c, c->d, c->ad, true));
     } else if (ll_path) {
         pcg_init_p2p_kernel<<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials, c->p2p);
         c->launches++;
-        LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+        LPF_TRY(apply_full(c, true, c->d, c->ad, c->den_slots, &c->st->status, false));
         LPF_TRY(halo_ll(c, false, c->ad, true));
     } else if (multi) {
         pcg_init_kernel<true><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, c->owned, c->r, c->z, c->d, c->ad, c->st, c->partials);
@@ -1244,8 +1145,8 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
         pcg_init_kernel<false><<<g, 256, 0, c->stream>>>(n, c->Bv, t, c->dinv, nullptr, c->r, c->z, c->d, c->ad, c->st, c->partials);
         c->launches++;
     }
-    if (!p2p_fused(c) && !ll_path) {
-        LPF_TRY(apply_launch<false>(c, c->gmap_c, c->d, c->ad, c->den_slots, &c->st->status));
+    if (!fused && !ll_path) {
+        LPF_TRY(apply_full(c, true, c->d, c->ad, c->den_slots, &c->st->status, false));
         LPF_TRY(ess_fix(c));
         if (multi) {
             LPF_TRY(halo_sum(c, c->halo, c->ad));
@@ -1277,6 +1178,10 @@ int pcg_run(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, bool zero_
     if (slot ^ 1) c->st_host[0] = c->st_host[1];
     LPF_TRY(pcg_l2_window(c, false));
     const PcgState &s = *c->st_host;
+    if (s.comm_error || s.status == PCG_COMM_ERROR) {
+        lpf::set_error("PCG: a flag wait of the peer-memory exchange timed out (a neighbour rank stalled or left the solve early)");
+        return LPF_ERR_COMM;
+    }
     // applies: 1 for the first A d (if the solve got that far) + one per completed direction update
     if (!(s.status == PCG_CONVERGED && s.final_iter == 0) && s.status != PCG_NOT_PD) applies += 1;
     applies += std::max(0, s.iter - 1) - (s.status == PCG_MAXITER ? 1 : 0);
@@ -1294,8 +1199,7 @@ int solve_from_X(lpf_ctx *c, double rel_tol, double abs_tol, int max_iter, lpf_p
 {
     // FormLinearSystem: c->X holds [0 ; x_ess].  B = -A X (unconstrained), B[ess] = X[ess]   (EliminateRHS)
     const int n = c->ndof;
-    CUDA_TRY(cudaMemsetAsync(c->tmp, 0, sizeof(double) * n, c->stream));
-    LPF_TRY(apply_launch<false>(c, c->gmap, c->X, c->tmp, nullptr, nullptr));
+    LPF_TRY(apply_full(c, false, c->X, c->tmp, nullptr, nullptr, true));
     LPF_TRY(halo_sum(c, c->halo, c->tmp));
     negate_kernel<<<vec_grid(n, c->sm_count), 256, 0, c->stream>>>(n, c->tmp, c->Bv);
     c->launches++;
@@ -1510,7 +1414,7 @@ int lpf_time_apply(lpf_ctx *c, const double *x, double *y, int reps, float *ms_t
     if (n_launches) *n_launches = c->launches - l0;
     if (ms_kernel) {
         CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
-        for (int i = 0; i < reps; i++) LPF_TRY(apply_launch<false>(c, c->gmap_c, x, y, nullptr, nullptr));
+        for (int i = 0; i < reps; i++) LPF_TRY(apply_launch(c, c->gmap_c, x, y, nullptr, nullptr));
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         CUDA_TRY(cudaEventSynchronize(c->ev1));
         CUDA_TRY(cudaEventElapsedTime(ms_kernel, c->ev0, c->ev1));

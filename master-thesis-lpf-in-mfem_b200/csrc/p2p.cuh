@@ -14,92 +14,8 @@
 // they carry the monotonically increasing sequence number.
 // Spin loops are bounded: on time-out they raise P2PLocal::error instead of hanging the GPU.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
+#include "p2p_dev.cuh"
 #include "vec_kernels.cuh"
-
-#define LPF_P2P_MAXR 16
-#define LPF_P2P_SPIN_LIMIT (1ll << 27)
-
-struct __align__(16) P2PBox {
-    uint4 red_ll[2][LPF_P2P_MAXR];                      // [parity][source rank] LL lines of the scalar all-reduce
-    long long ll_byte_off[2][2];                        // [plan][parity] byte offset of the LL halo receive areas
-    int off_for_src[2][LPF_P2P_MAXR];                   // [plan][source rank]: where that rank writes in MY recv buffer
-};
-
-struct P2PLocal {
-    unsigned long long red_seq;
-    int error;
-    unsigned long long ll_seq[2];      // LL halo exchanges done, per plan
-    unsigned int ll_counter[2];
-};
-
-struct P2PPlanDev {                    // device-side view of one halo plan
-    int n_nbr, total, n_shared;
-    const int *nbr_rank;               // [n_nbr]
-    const int *nbr_offset;             // [n_nbr+1]
-    const int *send_dofs;              // [total]
-    const int *send_nbr;               // [total] neighbour index of each send entry
-    const int *shared, *red_off, *red_src;
-    // LL protocol (p2p_halo_ll_kernel): per shared dof i the (neighbour, position) pairs it is sent to
-    const int *snd_off, *snd_nbr, *snd_pos;    // [n_shared+1], [total], [total]
-    uint4 *const *ll_dst;              // [2 parities][n_nbr] where I write LL lines in each neighbour's box
-    const uint4 *ll_recv[2];           // my LL receive areas
-};
-
-struct P2PDev {
-    int nranks, rank;
-    P2PBox *const *peers;              // [nranks] device pointers to every rank's box (incl. mine)
-    P2PBox *mine;
-    P2PLocal *local;
-};
-
-// ---- LL ("low latency") lines: 8 data bytes + two copies of a 32-bit sequence flag in ONE 16-byte store.  The
-// receiver polls the line itself; when both flags carry the expected sequence number both data halves have
-// landed (NVLink guarantees 8-byte atomicity), so no fence, no separate flag write and no second round trip is
-// needed -- the exchange costs one one-way NVLink latency (same idea as NCCL's LL protocol).
-__device__ __forceinline__ void ll_store(uint4 *p, double v, uint32_t flag)
-{
-    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)b), "r"(flag),
-                 "r"((uint32_t)(b >> 32)), "r"(flag) : "memory");
-}
-__device__ __forceinline__ double ll_poll(const uint4 *p, uint32_t flag, int *err)
-{
-    uint32_t a, fa, b, fb;
-    long long n = 0;
-    for (;;) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(p) : "memory");
-        if (fa == flag && fb == flag) break;
-        if (++n > LPF_P2P_SPIN_LIMIT) { *err = 1; return 0.0; }
-    }
-    return __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
-}
-__device__ __forceinline__ uint32_t ll_flag(unsigned long long seq) { return (uint32_t)(seq % 0xFFFFFFFFull) + 1u; }
-
-// Sum of one double over all ranks, executed by one full warp: lane r writes this rank's value as one LL line into
-// rank r's box and polls the line rank r writes into mine.  Returns the sum (identical bits on every rank: fixed
-// rank order) in every lane.  Two parities: a rank can start exchange k+2 only after every peer finished k.
-__device__ __forceinline__ double p2p_allreduce_warp(const P2PDev &d, double local_val)
-{
-    const int lane = threadIdx.x & 31;
-    const unsigned long long seq = d.local->red_seq + 1;
-    const int par = (int)(seq & 1);
-    const uint32_t flag = ll_flag(seq);
-    __syncwarp();
-    double got = 0.0;
-    if (lane < d.nranks) {
-        ll_store(&d.peers[lane]->red_ll[par][d.rank], local_val, flag);
-        got = ll_poll(&d.mine->red_ll[par][lane], flag, &d.local->error);
-    }
-    double s = 0.0;
-    for (int r = 0; r < d.nranks; r++) s += __shfl_sync(0xffffffffu, got, r);
-    __syncwarp();
-    if (lane == 0) d.local->red_seq = seq;
-    __syncwarp();
-    return s;
-}
 
 // ---- scalar all-reduce (sum) + what the PCG does with the result -----------------------------------------
 enum { P2P_RED_PLAIN = 0, P2P_RED_NOM = 1, P2P_RED_BETA = 2, P2P_RED_DEN = 3 };
@@ -123,6 +39,7 @@ __global__ void p2p_allreduce_kernel(P2PDev d, double *val, int mode, PcgState *
         else if (mode == P2P_RED_BETA) { if (st->status == PCG_RUNNING) pcg_finalize_beta(st, s); }
         else if (mode == P2P_RED_DEN) st->red[1] = s;
         else *val = s;
+        p2p_flag_error(d, st);
     }
 }
 
@@ -169,64 +86,7 @@ __global__ void p2p_halo_ll_kernel(P2PDev d, P2PPlanDev h, int plan, double *__r
         is_last = (t == gridDim.x - 1);
     }
     __syncthreads();
-    if (is_last && threadIdx.x == 0) d.local->ll_seq[plan] = seq;
-}
-
-// ---- halo-sum + (d, A d) all-reduce fused into the tail of the apply kernel ---------------------------------
-// Every CTA of the persistent apply kernel calls p2p_apply_tail() after its last batch.  The CTA that arrives
-// last (all scatter-adds of this rank are then globally visible) packs the interface values straight into the
-// neighbours' mailboxes, raises their flags, waits for theirs, adds the partial sums in rank order and finally
-// all-reduces the PCG denominator -- the collective rides on the compute kernel, no extra launch, no NCCL.
-struct P2PTail {
-    int enabled, with_den;
-    P2PDev d;
-    P2PPlanDev h;
-    PcgState *st;
-    double *den_slots;
-    unsigned int *done;
-};
-
-__device__ __forceinline__ void p2p_apply_tail(const P2PTail &t, double *__restrict__ y)
-{
-    __shared__ bool tail_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned int n = atomicInc(t.done, gridDim.x - 1);
-        tail_last = (n == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!tail_last) return;
-    __threadfence();
-    const int tid = threadIdx.x, nt = blockDim.x;
-    const P2PPlanDev &h = t.h;
-    // same LL lines and sequence numbers as p2p_halo_ll_kernel, so a rank with a small interface (tail) and a
-    // neighbour with a large one (separate kernel) interoperate
-    const unsigned long long seq = t.d.local->ll_seq[0] + 1;
-    const int par = (int)(seq & 1);
-    const uint32_t flag = ll_flag(seq);
-    for (int i = tid; i < h.n_shared; i += nt) {
-        const double own = __ldcg(y + h.shared[i]);
-        for (int k = h.snd_off[i]; k < h.snd_off[i + 1]; k++) ll_store(h.ll_dst[par * h.n_nbr + h.snd_nbr[k]] + h.snd_pos[k], own, flag);
-    }
-    if (t.with_den && tid < 32) {
-        double s = 0.0;
-        for (int i = tid; i < LPF_DEN_SLOTS; i += 32) { s += __ldcg(t.den_slots + i); t.den_slots[i] = 0.0; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        const double tot = p2p_allreduce_warp(t.d, s);
-        if (tid == 0) t.st->red[1] = tot;
-    }
-    const uint4 *recv = h.ll_recv[par];
-    for (int i = tid; i < h.n_shared; i += nt) {
-        const int dof = h.shared[i];
-        const double own = __ldcg(y + dof);
-        double s = 0.0;
-        for (int j = h.red_off[i]; j < h.red_off[i + 1]; j++) s += (h.red_src[j] < 0) ? own : ll_poll(recv + h.red_src[j], flag, &t.d.local->error);
-        y[dof] = s;
-    }
-    __syncthreads();
-    if (tid == 0 && h.n_nbr > 0) t.d.local->ll_seq[0] = seq;
+    if (is_last && threadIdx.x == 0) { d.local->ll_seq[plan] = seq; p2p_flag_error(d, st); }
 }
 
 // ---- PCG vector kernels with the cross-rank reduction inside (last block = one flag round trip, no extra launch) ----
@@ -248,7 +108,7 @@ __global__ void pcg_init_p2p_kernel(int n, const double *__restrict__ b, const d
         __syncthreads();
         if (threadIdx.x < 32) {
             const double tot = p2p_allreduce_warp(pd, loc);
-            if (threadIdx.x == 0) pcg_finalize_nom(st, tot);
+            if (threadIdx.x == 0) { pcg_finalize_nom(st, tot); p2p_flag_error(pd, st); }
         }
     }
 }
@@ -281,7 +141,7 @@ __global__ void pcg_update_p2p_kernel(int n, double *__restrict__ x, double *__r
         __syncthreads();
         if (threadIdx.x < 32) {
             const double tot = p2p_allreduce_warp(pd, loc);
-            if (threadIdx.x == 0) { st->den = den; pcg_finalize_beta(st, tot); }
+            if (threadIdx.x == 0) { st->den = den; pcg_finalize_beta(st, tot); p2p_flag_error(pd, st); }
         }
     }
 }

@@ -7,20 +7,12 @@
 // additions: 26 instead of 30 FP64 operations per line at p = 4, 64 instead of 90 at p = 8, and half as many
 // coefficient loads (LDCU) -- the two instruction classes that made the kernel issue-bound (ncu: 46 % DFMA,
 // 25 % LDCU, profiles/r01_apply_ncu.md).  The half-size tables are built on the host from B and G
-// (lpf_device.cu, fill_eo_tables) directly from their definitions:
+// (apply_order.cu, lpf_apply_tables) directly from their definitions:
 //   forward   out[q] = sum_d M[q][d] in[d]:  MeF[q][d] = (M[q][d] + M[q][D-1-d]) / 2, MoF[q][d] = (M[q][d] - M[q][D-1-d]) / 2
 //   transpose out[d] = sum_q M[q][d] in[q]:  MeT[d][q] = (M[q][d] + M[Q-1-q][d]) / 2, MoT[d][q] = (M[q][d] - M[Q-1-q][d]) / 2
 // (middle columns un-halved), and  out[j] = se + so,  out[N-1-j] = sigma (se - so)  with sigma = +1 for B, -1 for G.
 #pragma once
 #include "pa_apply_tma.cuh"
-
-struct LpfEoTab {
-    static constexpr int MH = (LPF_MAXP + 3) / 2;     // ceil(Q_max / 2)
-    double BeF[MH * MH], BoF[MH * MH], GeF[MH * MH], GoF[MH * MH];   // [QC][DC], [QC][DH]
-    double BeT[MH * MH], BoT[MH * MH], GeT[MH * MH], GoT[MH * MH];   // [DC][QC], [DC][QH]
-};
-
-__constant__ LpfEoTab c_eo[LPF_MAXP + 1];
 
 // out (+)= M in for a (anti)symmetric NO x NI matrix given by its even / odd half tables.
 template <int NI, int NO, int SIGN, bool ACC>
@@ -62,15 +54,18 @@ __device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N +
 // 87 % of the kernel's HBM bytes at order 4 -- disappears and the kernel becomes FP64-issue-bound.  Used automatically
 // when every element of the mesh is affine (all wave tanks of the reference); reported separately from the graded
 // stored-q-data number.
-template <int P, int E, bool DEN, int MINB, bool AFF = false>
+template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
-pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
-                   double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status,
-                    const P2PTail tail)
+pa_apply_eo_kernel(const ApplyKArgs ka)
 {
     using C = TmaCfg<P, E, AFF>;
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
-    constexpr int DP3 = C::DP3, QE = C::QE;
+    constexpr int DP3 = C::DP3, QE = C::QE, D3 = C::D3;
+    const double *__restrict__ qd = ka.qd;
+    const int *__restrict__ gmap = ka.gmap;
+    const double *__restrict__ x = ka.x;
+    double *__restrict__ y = ka.y;
+    const int ne = ka.ne;
     constexpr int DC = (D + 1) / 2, DH = D / 2 > 0 ? D / 2 : 1, QC = (Q + 1) / 2, QH = Q / 2 > 0 ? Q / 2 : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sq = reinterpret_cast<double *>(smem_raw + C::OFF_Q);
@@ -112,11 +107,13 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
     // the tail of the previous kernel.  x, y and the PCG status are produced by that kernel: wait for it here.
     griddep_wait();
     griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
-    if (status != nullptr && *status != 0) {      // solve already finished: drain the copies issued above and leave
+    if (ka.status != nullptr && *ka.status != 0) {      // solve already finished: drain the copies issued above and leave
         mbar_wait(bar_i, 0);
         if (!AFF) mbar_wait(bar_q, 0);
         return;
     }
+    P2POverlap ov;
+    if (ka.tail.mode == 2) p2p_if_begin(ka.tail, ov);
     double xs[D], xsn[D];
     double part = 0.0;
     mbar_wait(bar_i, 0);
@@ -139,7 +136,7 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
         const int cur = it & 1, nxt = cur ^ 1;
         // loop-variant (always zero) table offset: keeps the compiler from hoisting the coefficients out of the
         // batch loop into (too few) uniform registers, see pa_apply_tma.cuh
-        const LpfEoTab &T = c_eo[P + (it >> 30)];
+        const LpfOrderTab<P> &T = c_ot[it >> 30];
         double da[6];                                   // AFF: element tensor, loaded two stages before its use
         if (AFF && zvalid) {
             const double *de = qd + (size_t)(e0 + ez) * 6;
@@ -206,12 +203,11 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
                 eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, g2);
             }
             if (AFF) {
-                const LpfBasisTab &W = c_tab[P + (it >> 30)];
                 const int qy = q2 / Q, qx = q2 - qy * Q;
-                const double wxy = W.qwts[qx] * W.qwts[qy];
+                const double wxy = T.qwts[qx] * T.qwts[qy];
 #pragma unroll
                 for (int qz = 0; qz < Q; qz++) {
-                    const double w = wxy * W.qwts[qz];
+                    const double w = wxy * T.qwts[qz];
                     const double a0 = g0[qz], a1 = g1[qz], a2 = g2[qz];
                     g0[qz] = w * (da[0] * a0 + da[1] * a1 + da[2] * a2);
                     g1[qz] = w * (da[1] * a0 + da[3] * a1 + da[4] * a2);
@@ -296,8 +292,9 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
 #pragma unroll
             for (int i = 0; i < D; i++) {
                 const int g = gi[i];
+                if (DET) ka.yE[(size_t)(e0 + ex) * D3 + lx * D + i] = yv[i];
                 if (g >= 0) {
-                    red_add_f64(y + g, yv[i]);
+                    if (!DET) red_add_f64(y + g, yv[i]);
                     if (DEN) part = fma(xs[i], yv[i], part);
                 }
             }
@@ -306,22 +303,11 @@ pa_apply_eo_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, 
 #pragma unroll
             for (int i = 0; i < D; i++) xs[i] = xsn[i];
         }
-        __syncthreads();
+        apply_batch_end(ka.tail, ov, b, y);
     }
 
-    if (DEN && den_slots != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        __shared__ double wsum[32];
-        const int w = tid >> 5, nw = (C::NT + 31) >> 5;
-        if ((tid & 31) == 0) wsum[w] = part;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int i = 0; i < nw; i++) s += wsum[i];
-            atomicAdd(den_slots + (blockIdx.x & 255), s);
-        }
-    }
-    // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, fused into this kernel's tail
-    if (tail.enabled) p2p_apply_tail(tail, y);
+    if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots);
+    // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, riding on this kernel
+    if (ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
+    else if (ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
 }

@@ -4,6 +4,15 @@
 // a7+a8 of SURVEY.md 8a: ElementRestriction::Mult + DiffusionIntegrator::AddMultPA +
 // ElementRestriction::MultTranspose (+ the essential-dof masks of ConstrainedOperator) in one kernel.
 //
+// Apply kernel: E elements per CTA, Q^2 threads per element, "one thread per 1-D line":
+//   X  stage: thread (dz,dy) gathers D dofs from x_L, forms B_x u and G_x u (Q values each) -> smem A
+//   Y  stage: thread (dz,qx) contracts along y -> BB, BG, GB (Q values each)               -> smem B
+//   Z  stage: thread (qy,qx) contracts along z, applies the 3x3 symmetric q-data tensor level by
+//             level and contracts back along z entirely in registers                        -> smem B
+//   Yt stage: thread (dz,qx) -> smem A;   Xt stage: thread (dz,dy) -> D results, scatter-added to y_L.
+// Each thread loads D (or Q) values and performs D*Q (or 2-3x that) FMAs on them, so shared-memory
+// traffic per FMA is ~4x lower than in a thread-per-point scheme.
+//
 // Each CTA loops over batches of E consecutive elements (grid = resident CTAs x SMs).  One batch's q-data
 // is ONE contiguous 48 Q^3 E-byte block in HBM (layout [e][qz][c2][q2][2], see pa_kernels.cuh), so a single
 // elected thread moves it with one bulk copy; the copy for batch b' = b + gridDim.x is issued as soon as
@@ -13,84 +22,58 @@
 // not depend on occupancy to hide HBM latency (ncu of the non-pipelined kernel: 34 % long-scoreboard, 26 %
 // barrier stalls -- profiles/r01_apply_ncu.md).
 #pragma once
-#include "pa_kernels.cuh"
-#include "p2p.cuh"
+#include "apply_cfg.cuh"
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+// ---- pieces shared by the persistent kernels ----
+// x_e . y_e partial of this CTA -> its (d, A d) slot (one slot per CTA: grids are capped at LPF_DEN_SLOTS)
+template <int NT>
+__device__ __forceinline__ void apply_den_epilogue(double part, double *__restrict__ den_slots)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-// Same copy with an L2 evict-first policy: q-data and gather maps are read exactly once per apply, so they should not
-// push the vectors (x gathered / y scatter-added by up to 8 elements each, and reused by the next PCG kernels) out of L2.
-__constant__ int c_l2_stream_hint = 1;      // option "l2_hint": 1 = evict-first for the streamed data, 0 = default policy
-__device__ __forceinline__ uint64_t l2_evict_first_policy()
-{
-    uint64_t pol;
-    if (c_l2_stream_hint) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ void bulk_g2s_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t pol)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    part = warp_sum_partial(part, NT);
+    __shared__ double wsum[32];
+    const int tid = threadIdx.x, w = tid >> 5, nw = (NT + 31) >> 5;
+    if ((tid & 31) == 0) wsum[w] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int i = 0; i < nw; i++) s += wsum[i];
+        atomicAdd(den_slots + (blockIdx.x & (LPF_DEN_SLOTS - 1)), s);
+    }
 }
 
-template <int P, int E, bool AFF = false>      // AFF: affine fast path, no q-data staging area (pa_apply_eo.cuh)
-struct TmaCfg : ApplyCfg<P, E> {
-    using B = ApplyCfg<P, E>;
-    static constexpr int D3 = B::D * B::D * B::D;
-    static constexpr int DP3 = (D3 + 3) & ~3;                       // gather-map row padded to 16 bytes
-    static constexpr int QE = 6 * B::Q * B::Q * B::Q;               // doubles of q-data per element
-    // byte offsets inside dynamic shared memory
-    static constexpr size_t OFF_Q = 0;                                                  // [E][QE] doubles (16B aligned)
-    static constexpr size_t OFF_IDX = OFF_Q + (AFF ? (size_t)0 : (size_t)E * QE * 8);   // [2][E][DP3] ints
-    static constexpr size_t OFF_WORK = (OFF_IDX + (size_t)2 * E * DP3 * 4 + 15) & ~(size_t)15;
-    static constexpr size_t OFF_BAR = (OFF_WORK + (size_t)E * B::ES * 8 + 15) & ~(size_t)15;   // 3 mbarriers
-    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
-};
+// end of one batch: the __syncthreads that frees the stage buffers for the next batch, plus (multi-GPU, overlapped halo
+// exchange) the bookkeeping of the interface batches
+__device__ __forceinline__ void apply_batch_end(const P2PTail &tail, P2POverlap &ov, int b, const double *__restrict__ y)
+{
+    if (tail.mode == 2) {
+        const bool ifb = b < tail.n_if_batches;
+        if (ifb) __threadfence();
+        __syncthreads();
+        if (ifb && threadIdx.x == 0) atomicAdd(&tail.d.local->if_done, 1u);
+        p2p_if_try_send(tail, ov, y);
+    } else {
+        __syncthreads();
+    }
+}
 
-template <int P, int E, bool DEN, int MINB>
+template <int P, int E, bool DEN, int MINB, bool DET = false>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
-pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
-                    double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status,
-                    const P2PTail tail)
+pa_apply_tma_kernel(const ApplyKArgs ka)
 {
     using C = TmaCfg<P, E>;
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
-    constexpr int DP3 = C::DP3, QE = C::QE;
+    constexpr int DP3 = C::DP3, QE = C::QE, D3 = C::D3;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sq = reinterpret_cast<double *>(smem_raw + C::OFF_Q);
     int *sidx = reinterpret_cast<int *>(smem_raw + C::OFF_IDX);
     double *smem = reinterpret_cast<double *>(smem_raw + C::OFF_WORK);
     uint64_t *bar_q = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
     uint64_t *bar_i = bar_q + 1;      // two of them
+    const double *__restrict__ qd = ka.qd;
+    const int *__restrict__ gmap = ka.gmap;
+    const double *__restrict__ x = ka.x;
+    double *__restrict__ y = ka.y;
+    const int ne = ka.ne;
 
     const int tid = threadIdx.x;
     const int nb = (ne + E - 1) / E;
@@ -125,11 +108,13 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
     // the tail of the previous kernel.  x, y and the PCG status are produced by that kernel: wait for it here.
     griddep_wait();
     griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
-    if (status != nullptr && *status != 0) {      // solve already finished: drain the copies issued above and leave
+    if (ka.status != nullptr && *ka.status != 0) {      // solve already finished: drain the copies issued above and leave
         mbar_wait(bar_i, 0);
         mbar_wait(bar_q, 0);
         return;
     }
+    P2POverlap ov;
+    if (ka.tail.mode == 2) p2p_if_begin(ka.tail, ov);
     double xs[D], xsn[D];
     double part = 0.0;
     mbar_wait(bar_i, 0);
@@ -153,7 +138,7 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
         // The basis tables are addressed through a loop-variant (always zero) offset: without it the compiler
         // hoists all 60 B/G coefficients out of the batch loop, overflows the uniform register file and pays
         // ~480 R2UR/MOV instructions per element shuffling them back (ncu source page, profiles/r01_apply_ncu.md).
-        const LpfBasisTab &T = c_tab[P + (it >> 30)];
+        const LpfOrderTab<P> &T = c_ot[it >> 30];
 #define BGL(q, i) (reinterpret_cast<const double2 *>(T.BG)[(q) * D + (i)])     /* {B, G}[q][i]: one LDCU.128 */
 
         // gather map of the next batch -> the other index buffer (last read two stages ago, before a barrier)
@@ -293,8 +278,9 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
 #pragma unroll
                 for (int q = 0; q < Q; q++) { const double2 c = BGL(q, i); s = fma(c.x, ta[q], s); s = fma(c.y, tb[q], s); }
                 const int g = gi[i];
+                if (DET) ka.yE[(size_t)(e0 + ex) * D3 + lx * D + i] = s;
                 if (g >= 0) {
-                    red_add_f64(y + g, s);
+                    if (!DET) red_add_f64(y + g, s);
                     if (DEN) part = fma(xs[i], s, part);
                 }
             }
@@ -303,23 +289,12 @@ pa_apply_tma_kernel(const double *__restrict__ qd, const int *__restrict__ gmap,
 #pragma unroll
             for (int i = 0; i < D; i++) xs[i] = xsn[i];
         }
-        __syncthreads();     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
+        apply_batch_end(ka.tail, ov, b, y);     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
 #undef BGL
     }
 
-    if (DEN && den_slots != nullptr) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        __shared__ double wsum[32];
-        const int w = tid >> 5, nw = (C::NT + 31) >> 5;
-        if ((tid & 31) == 0) wsum[w] = part;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int i = 0; i < nw; i++) s += wsum[i];
-            atomicAdd(den_slots + (blockIdx.x & 255), s);
-        }
-    }
-    // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, fused into this kernel's tail
-    if (tail.enabled) p2p_apply_tail(tail, y);
+    if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots);
+    // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, riding on this kernel
+    if (ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
+    else if (ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
 }

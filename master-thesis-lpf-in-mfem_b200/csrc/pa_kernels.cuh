@@ -1,7 +1,7 @@
 // sm_100a kernels for the partial-assembly DiffusionIntegrator on H1 hexes.
 //
 //   pa_setup_kernel   a1  DiffusionIntegrator::AssemblePA  (Solvers/PF_linear_par_partial.cpp:118-121)
-//   pa_apply_kernel   a7+a8 (+a5 masks)  ElementRestriction::Mult + AddMultPA + MultTranspose fused
+//   (apply kernels: pa_apply_tma.cuh / pa_apply_eo.cuh / pa_apply_evec.cuh, one translation unit per order)
 //   pa_diag_kernel    a2  AssembleDiagonalPA + restriction-transpose (:124)
 //
 // q-data layout in HBM (internal, produced by pa_setup_kernel):
@@ -20,23 +20,11 @@
 // traffic per FMA is ~4x lower than in a thread-per-point scheme; B/G come from constant memory as
 // immediate operands of the unrolled FMAs.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "dev_util.cuh"
 
-// Scatter-add without a return value: always the fire-and-forget reduction (SASS REDG), never the round-trip ATOMG.
-// (With plain atomicAdd the compiler switched to ATOMG as soon as the kernel also read y elsewhere -- the fused
-// halo tail -- which cost 30 % of the apply kernel's bandwidth; profiles/r01_apply_ncu.md.)
-__device__ __forceinline__ void red_add_f64(double *addr, double v)
-{
-    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-}
-
-#define LPF_MAXP 8
-
+// 1-D tables of one order for the generic (order as a run-time argument) kernels of this file and of vec_kernels.cuh.
+// The apply kernels keep their own per-order tables (apply_cfg.cuh).
 struct __align__(16) LpfBasisTab {
-    // {B, G} interleaved per (q, d): one 16-byte uniform load (LDCU.128) feeds both FMAs that every stage
-    // issues on the same (q, d) pair -- halves the coefficient loads of the apply kernels
-    double BG[2 * (LPF_MAXP + 2) * (LPF_MAXP + 1)];
     double B[(LPF_MAXP + 2) * (LPF_MAXP + 1)];     // [Q][D]
     double G[(LPF_MAXP + 2) * (LPF_MAXP + 1)];
     double Dhat[(LPF_MAXP + 1) * (LPF_MAXP + 1)];  // [D][D]
@@ -45,15 +33,7 @@ struct __align__(16) LpfBasisTab {
     double qwts[LPF_MAXP + 2];
 };
 
-__constant__ LpfBasisTab c_tab[LPF_MAXP + 1];
-
-__host__ __device__ constexpr int lpf_pad_to(int v, int target_mod16)
-{
-    // smallest w >= v with w % 16 == target_mod16 % 16
-    int w = v;
-    while ((w & 15) != (target_mod16 & 15)) w++;
-    return w;
-}
+static __constant__ LpfBasisTab c_tab[LPF_MAXP + 1];
 
 // Affine fast path set-up: one thread per element.  qa[e][6] = (D11, D21, D31, D22, D32, D33) of detJ J^-1 J^-T (no
 // quadrature weight) from the constant Jacobian of an affine hex; *not_affine is raised if any element's trilinear map
@@ -84,224 +64,6 @@ __global__ void pa_affine_setup_kernel(int ne, const double *__restrict__ corner
     q[3] = s * (A21 * A21 + A22 * A22 + A23 * A23);
     q[4] = s * (A21 * A31 + A22 * A32 + A23 * A33);
     q[5] = s * (A31 * A31 + A32 * A32 + A33 * A33);
-}
-
-// Strides of the two stage buffers, per order, picked by the bank-conflict model tools/smem_layout_sim.py (shared-memory
-// wavefronts per element, old formula-padded layout -> this table):  p1 48 -> 32, p2 90 -> 63, p3 230 -> 167, p4 319 -> 322
-// (smaller: 4 CTAs per SM), p5 560 -> 496, p6 680 -> 642, p7 1006 -> 862, p8 1394 -> 1394 (smaller).  Measured at order 3:
-// 77 % -> 89 % of the HBM roofline from the layout alone.
-//   {SAY, SAZ, SBZ, PAD}: A = [arr 2][dz][dy][qx] with strides SAZ, SAY, 1; B = [arr 3][dz][qy][qx] with strides SBZ, Q, 1
-__host__ __device__ constexpr int lpf_smem_stride(int p, int which)
-{
-    constexpr int T[9][4] = {{0, 0, 0, 0}, {4, 8, 12, 1}, {5, 20, 20, 0}, {5, 28, 26, 1}, {7, 35, 38, 12},
-                             {7, 42, 55, 4}, {9, 72, 72, 0}, {10, 89, 89, 0}, {10, 90, 106, 0}};
-    return T[p][which];
-}
-
-template <int P, int E>
-struct ApplyCfg {
-    static constexpr int D = P + 1, Q = P + 2;
-    static constexpr int LX = D * D, LY = D * Q, LZ = Q * Q;
-    static constexpr int NT = E * LZ;
-    static constexpr int DP3 = (D * D * D + 3) & ~3;    // gather-map row stride (rows padded to 16 bytes for bulk copies)
-    static constexpr int SAY = lpf_smem_stride(P, 0);
-    static constexpr int SAZ = lpf_smem_stride(P, 1);
-    static constexpr int SAA = D * SAZ;
-    static constexpr int SBZ = lpf_smem_stride(P, 2);
-    static constexpr int SBA = D * SBZ;
-    static constexpr int ES = 2 * SAA + 3 * SBA + lpf_smem_stride(P, 3);      // element stride
-    static constexpr int OFFB = 2 * SAA;
-    static constexpr size_t SMEM_BYTES = (size_t)E * ES * sizeof(double);
-    static_assert(SAY >= Q && SAZ >= D * SAY - (SAY - Q) && SBZ >= Q * Q, "stage-buffer strides too small");
-};
-
-__device__ __forceinline__ double2 ldg_stream2(const double2 *p)
-{
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-}
-
-// MODE bit 0: accumulate per-CTA x_e . y_e into den_slots (PCG denominator)
-// EVEC: x/y are E-vectors (AddMultPA semantics: y_E += ...), gmap unused.
-template <int P, int E, bool PREFETCH, bool EVEC, int MINB>
-__global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
-pa_apply_kernel(const double *__restrict__ qd, const int *__restrict__ gmap, const double *__restrict__ x,
-                double *__restrict__ y, int ne, double *__restrict__ den_slots, const int *__restrict__ status)
-{
-    using C = ApplyCfg<P, E>;
-    constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
-    constexpr int D3 = D * D * D;
-    extern __shared__ double smem[];
-    if (status != nullptr && *status != 0) return;     // PCG already finished: graph-replayed launch is a no-op
-    const LpfBasisTab &T = c_tab[P];
-    const int tid = threadIdx.x;
-    const int e0 = blockIdx.x * E;
-
-    // ---- Z-role bookkeeping + early q-data loads (latency hidden behind the X and Y stages) ----
-    const int ez = tid / LZ, q2 = tid - ez * LZ;
-    const bool zvalid = (e0 + ez) < ne;
-    const double2 *qsrc = reinterpret_cast<const double2 *>(qd) + ((size_t)(e0 + ez) * Q * 3) * LZ + q2;
-    double2 qv[PREFETCH ? Q : 1][3];
-    if (PREFETCH && zvalid) {
-#pragma unroll
-        for (int qz = 0; qz < Q; qz++)
-#pragma unroll
-            for (int c = 0; c < 3; c++) qv[qz][c] = ldg_stream2(qsrc + (qz * 3 + c) * LZ);
-    }
-
-    // ---- X stage: line (dz,dy) ----
-    int idx[D];
-    double xs[D];
-    const int ex = tid / LX, lx = tid - ex * LX;
-    const int xdz = lx / D, xdy = lx - xdz * D;
-    const bool xvalid = (tid < E * LX) && (e0 + ex) < ne;
-    if (xvalid) {
-        if (EVEC) {
-            const double *src = x + (size_t)(e0 + ex) * D3 + lx * D;
-#pragma unroll
-            for (int i = 0; i < D; i++) { idx[i] = 0; xs[i] = src[i]; }
-        } else {
-            const int *gi = gmap + (size_t)(e0 + ex) * C::DP3 + lx * D;
-#pragma unroll
-            for (int i = 0; i < D; i++) idx[i] = gi[i];
-#pragma unroll
-            for (int i = 0; i < D; i++) xs[i] = idx[i] >= 0 ? x[idx[i]] : 0.0;
-        }
-        double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            double sb = 0.0, sg = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; i++) { sb = fma(T.BG[2 * (q * D + i)], xs[i], sb); sg = fma(T.BG[2 * (q * D + i) + 1], xs[i], sg); }
-            a[q] = sb;
-            a[C::SAA + q] = sg;
-        }
-    }
-    __syncthreads();
-
-    // ---- Y stage: line (dz,qx) ----
-    const int ey = tid / LY, ly = tid - ey * LY;
-    const int ydz = ly / Q, yqx = ly - ydz * Q;
-    const bool yvalid = (tid < E * LY) && (e0 + ey) < ne;
-    if (yvalid) {
-        const double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
-        double ua[D], ub[D];
-#pragma unroll
-        for (int i = 0; i < D; i++) { ua[i] = a[i * C::SAY]; ub[i] = a[C::SAA + i * C::SAY]; }
-        double *b = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
-#pragma unroll
-        for (int q = 0; q < Q; q++) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; i++) {
-                s0 = fma(T.BG[2 * (q * D + i)], ua[i], s0);     // B_y B_x u
-                s1 = fma(T.BG[2 * (q * D + i) + 1], ua[i], s1);     // G_y B_x u
-                s2 = fma(T.BG[2 * (q * D + i)], ub[i], s2);     // B_y G_x u
-            }
-            b[q * Q] = s0;
-            b[C::SBA + q * Q] = s1;
-            b[2 * C::SBA + q * Q] = s2;
-        }
-    }
-    __syncthreads();
-
-    // ---- Z stage: column (qy,qx): forward z, q-data, backward z, all in registers ----
-    if (zvalid) {
-        double *b = smem + ez * C::ES + C::OFFB + q2;
-        double ubb[D], ubg[D], ugb[D], cbb[D], cbg[D], cgb[D];
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-            ubb[i] = b[i * C::SBZ]; ubg[i] = b[C::SBA + i * C::SBZ]; ugb[i] = b[2 * C::SBA + i * C::SBZ];
-            cbb[i] = 0.0; cbg[i] = 0.0; cgb[i] = 0.0;
-        }
-#pragma unroll
-        for (int qz = 0; qz < Q; qz++) {
-            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll
-            for (int i = 0; i < D; i++) {
-                g0 = fma(T.BG[2 * (qz * D + i)], ugb[i], g0);
-                g1 = fma(T.BG[2 * (qz * D + i)], ubg[i], g1);
-                g2 = fma(T.BG[2 * (qz * D + i) + 1], ubb[i], g2);
-            }
-            double2 d0, d1, d2;
-            if (PREFETCH) { d0 = qv[qz][0]; d1 = qv[qz][1]; d2 = qv[qz][2]; }
-            else {
-                d0 = ldg_stream2(qsrc + (qz * 3 + 0) * LZ);
-                d1 = ldg_stream2(qsrc + (qz * 3 + 1) * LZ);
-                d2 = ldg_stream2(qsrc + (qz * 3 + 2) * LZ);
-            }
-            // (D11, D21) (D31, D22) (D32, D33)
-            const double f0 = d0.x * g0 + d0.y * g1 + d1.x * g2;
-            const double f1 = d0.y * g0 + d1.y * g1 + d2.x * g2;
-            const double f2 = d1.x * g0 + d2.x * g1 + d2.y * g2;
-#pragma unroll
-            for (int i = 0; i < D; i++) {
-                cgb[i] = fma(T.BG[2 * (qz * D + i)], f0, cgb[i]);
-                cbg[i] = fma(T.BG[2 * (qz * D + i)], f1, cbg[i]);
-                cbb[i] = fma(T.BG[2 * (qz * D + i) + 1], f2, cbb[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-            b[i * C::SBZ] = cbb[i]; b[C::SBA + i * C::SBZ] = cbg[i]; b[2 * C::SBA + i * C::SBZ] = cgb[i];
-        }
-    }
-    __syncthreads();
-
-    // ---- Yt stage: line (dz,qx) ----
-    if (yvalid) {
-        const double *b = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
-        double vbb[Q], vbg[Q], vgb[Q];
-#pragma unroll
-        for (int q = 0; q < Q; q++) { vbb[q] = b[q * Q]; vbg[q] = b[C::SBA + q * Q]; vgb[q] = b[2 * C::SBA + q * Q]; }
-        double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-            double ta = 0.0, tb = 0.0;
-#pragma unroll
-            for (int q = 0; q < Q; q++) {
-                ta = fma(T.BG[2 * (q * D + i)], vbb[q], ta);
-                ta = fma(T.BG[2 * (q * D + i) + 1], vbg[q], ta);
-                tb = fma(T.BG[2 * (q * D + i)], vgb[q], tb);
-            }
-            a[i * C::SAY] = ta;
-            a[C::SAA + i * C::SAY] = tb;
-        }
-    }
-    __syncthreads();
-
-    // ---- Xt stage: line (dz,dy) + scatter-add ----
-    double part = 0.0;
-    if (xvalid) {
-        const double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
-        double ta[Q], tb[Q];
-#pragma unroll
-        for (int q = 0; q < Q; q++) { ta[q] = a[q]; tb[q] = a[C::SAA + q]; }
-        double *dst = y + (size_t)(e0 + ex) * D3 + lx * D;
-#pragma unroll
-        for (int i = 0; i < D; i++) {
-            double s = 0.0;
-#pragma unroll
-            for (int q = 0; q < Q; q++) { s = fma(T.BG[2 * (q * D + i)], ta[q], s); s = fma(T.BG[2 * (q * D + i) + 1], tb[q], s); }
-            if (EVEC) dst[i] += s;
-            else if (idx[i] >= 0) { red_add_f64(y + idx[i], s); part = fma(xs[i], s, part); }
-        }
-    }
-    if (den_slots != nullptr) {
-        // CTA-level sum of x_e . (A_e x_e): (d, A d) of the PCG without a second pass over the vectors
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        __shared__ double wsum[32];
-        const int w = tid >> 5, nw = (C::NT + 31) >> 5;
-        if ((tid & 31) == 0) wsum[w] = part;
-        __syncthreads();
-        if (tid == 0) {
-            double s = 0.0;
-            for (int i = 0; i < nw; i++) s += wsum[i];
-            atomicAdd(den_slots + (blockIdx.x & 255), s);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -381,7 +143,9 @@ __global__ void pa_qdata_export_kernel(int p, int ne, const double *__restrict__
     o[0] = a.x; o[Q3] = a.y; o[2 * Q3] = b.x; o[3 * Q3] = b.y; o[4 * Q3] = c.x; o[5 * Q3] = c.y;
 }
 
-// PA diagonal: one thread per element dof, scatter-added into the L-vector.
+// PA diagonal: one thread per element dof.  gmap != nullptr: scatter-added into the L-vector `diag`
+// (a2, restriction-transpose fused); gmap == nullptr: E-vector output diagE[e][D^3] += ... -- the semantics of
+// DiffusionIntegrator::AssembleDiagonalPA(Vector &diag) (accumulates), also the first half of the deterministic route.
 __global__ void pa_diag_kernel(int p, int ne, const double *__restrict__ qd, const int *__restrict__ gmap,
                                double *__restrict__ diag)
 {
@@ -407,6 +171,21 @@ __global__ void pa_diag_kernel(int p, int ne, const double *__restrict__ qd, con
             }
         }
     }
+    if (gmap == nullptr) { diag[gid] += acc; return; }
     const int g = gmap[(size_t)e * DP3 + d];
     atomicAdd(diag + (g >= 0 ? g : ~g), acc);
+}
+
+// Deterministic restriction-transpose (option "deterministic"): y[i] = sum of the E-vector entries of dof i, taken in
+// ascending (element, local node) order -- the order of MFEM's ElementRestriction::MultTranspose on the CPU, which walks
+// the same offsets / indices table.  `skip` (may be NULL) marks rows that stay 0 (essential dofs of the constrained map).
+__global__ void det_gather_kernel(int n, const int *__restrict__ offsets, const int *__restrict__ indices,
+                                  const double *__restrict__ yE, const uint8_t *__restrict__ skip, double *__restrict__ y)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    if (skip == nullptr || !skip[i])
+        for (int j = offsets[i]; j < offsets[i + 1]; j++) s += yE[indices[j]];
+    y[i] = s;
 }

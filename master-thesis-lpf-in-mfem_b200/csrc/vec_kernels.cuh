@@ -5,29 +5,8 @@
 // without host round trips -- once the stopping rule of CGSolver::Mult fires, the rest of the chunk
 // degenerates to empty launches and the iteration count stays exactly MFEM's.
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
-
-// Programmatic dependent launch (PDL): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
-// start while its predecessor in the stream is still draining; griddep_wait() blocks until the predecessor has
-// completed and its writes are visible, griddep_launch() lets the successor's CTAs be scheduled early.  Both are
-// no-ops for a kernel launched without the attribute.  Every kernel of the PCG iteration calls them, which hides
-// most of the 2-3 us launch + prologue latency between the three kernels of an iteration (small meshes are launch-bound).
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-enum { PCG_RUNNING = 0, PCG_CONVERGED = 1, PCG_MAXITER = 2, PCG_BREAKDOWN = 3, PCG_NOT_PD = 4 };
-
-#define LPF_DEN_SLOTS 256
-#define LPF_MAX_PARTIALS 2048
-
-struct PcgState {
-    double nom, den, betanom, r0, nom0, beta, rel2, abs2;
-    double red[4];              // staging for cross-rank reductions
-    int iter, status, max_iter, final_iter;
-    unsigned int counter;
-    int pad;
-};
+#include "dev_util.cuh"
+#include "p2p_types.hpp"
 
 __device__ __forceinline__ double block_sum(double v)
 {
@@ -47,6 +26,14 @@ __device__ __forceinline__ double block_sum(double v)
     }
     __syncthreads();
     return sh[32];
+}
+
+// this thread's share of the (d, A d) slots written by the apply kernel, in a fixed order (reproducible)
+__device__ __forceinline__ double den_slot_sum(const double *den_slots)
+{
+    double s = 0.0;
+    for (int i = threadIdx.x; i < LPF_DEN_SLOTS; i += blockDim.x) s += den_slots[i];
+    return s;
 }
 
 // Block partial -> global array; the last block to arrive sums the array in a fixed order and calls fin(sum).
@@ -96,8 +83,9 @@ __device__ __forceinline__ void pcg_finalize_beta(PcgState *st, double betanom)
 __global__ void pcg_reset_kernel(PcgState *st, double *den_slots, double rel_tol, double abs_tol, int max_iter)
 {
     const int t = threadIdx.x;
-    if (t < LPF_DEN_SLOTS) den_slots[t] = 0.0;
+    for (int i = t; i < LPF_DEN_SLOTS; i += blockDim.x) den_slots[i] = 0.0;
     if (t == 0) {
+        st->comm_error = 0;
         st->nom = st->den = st->betanom = st->r0 = st->nom0 = st->beta = 0.0;
         st->rel2 = rel_tol * rel_tol; st->abs2 = abs_tol * abs_tol;
         st->iter = 1; st->status = PCG_RUNNING; st->max_iter = max_iter; st->final_iter = 0; st->counter = 0;
@@ -129,8 +117,8 @@ __global__ void pcg_fin_beta_kernel(PcgState *st) { if (st->status == PCG_RUNNIN
 // multi-GPU: den_slots -> st->red[1] (then all-reduced into st->den by the host-enqueued collective)
 __global__ void pcg_den_local_kernel(PcgState *st, double *den_slots)
 {
-    const double s = block_sum(threadIdx.x < LPF_DEN_SLOTS ? den_slots[threadIdx.x] : 0.0);
-    if (threadIdx.x < LPF_DEN_SLOTS) den_slots[threadIdx.x] = 0.0;
+    const double s = block_sum(den_slot_sum(den_slots));
+    for (int i = threadIdx.x; i < LPF_DEN_SLOTS; i += blockDim.x) den_slots[i] = 0.0;
     if (threadIdx.x == 0) st->red[1] = s;
 }
 
@@ -146,7 +134,7 @@ __global__ void pcg_update_kernel(int n, double *__restrict__ x, double *__restr
     if (st->status != PCG_RUNNING) return;
     double den;
     if (MULTI) den = st->red[1];
-    else den = block_sum(threadIdx.x < LPF_DEN_SLOTS ? den_slots[threadIdx.x] : 0.0);
+    else den = block_sum(den_slot_sum(den_slots));
     if (den == 0.0) {                                  // CGSolver: den == 0 -> stop, final_iter = i
         if (blockIdx.x == 0 && threadIdx.x == 0) { st->den = den; st->status = PCG_BREAKDOWN; st->final_iter = st->iter > 1 ? st->iter : 0; }
         return;
@@ -176,7 +164,7 @@ __global__ void pcg_dir_kernel(int n, const double *__restrict__ z, double *__re
     griddep_launch();      // after the wait: at most ONE successor kernel is resident ahead of time
     if (st->status != PCG_RUNNING) return;
     const double beta = st->beta;
-    if (blockIdx.x == 0 && threadIdx.x < LPF_DEN_SLOTS) den_slots[threadIdx.x] = 0.0;
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < LPF_DEN_SLOTS; i += blockDim.x) den_slots[i] = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         d[i] = fma(beta, d[i], z[i]);
         ad[i] = 0.0;

@@ -2,7 +2,7 @@
 #pragma once
 #include <string>
 
-#define LPF_MAX_ORDER 8
+#define LPF_MAX_ORDER 10
 
 namespace lpf {
 void set_error(const std::string &s);

@@ -89,7 +89,7 @@ lpf_space *lpf_space_create(const lpf_mesh *m, int order, int ess_attr, int nran
 {
     try {
         if (!m) throw std::runtime_error("lpf_space_create: null mesh");
-        if (order < 1 || order > LPF_MAX_ORDER) throw std::runtime_error("lpf_space_create: order must be in 1..8");
+        if (order < 1 || order > LPF_MAX_ORDER) throw std::runtime_error("lpf_space_create: order must be in 1..10");
         auto s = std::make_unique<lpf_space>();
         s->order = order;
         s->mesh = &m->m;

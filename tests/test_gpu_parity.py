@@ -33,7 +33,7 @@ def tank(lpf):
     return lpf.Mesh.wave_tank(3, 1, 1).refine(1).perturb(0.15)
 
 
-@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 def test_qdata_apply_diag_all_orders(lpf, orc, cuda, tank, p):
     torch = cuda
     sp = lpf.Space(tank, p)
@@ -67,14 +67,17 @@ def test_qdata_apply_diag_all_orders(lpf, orc, cuda, tank, p):
     dg = torch.empty_like(xd)
     ctx.diag(dg)
     assert rel_err(dg.cpu().numpy(), A.diag()) < TOL_OP
+    # AssembleDiagonalPA: E-vector diagonal, accumulated
+    dE = torch.ones(sp.ne * (p + 1) ** 3, dtype=torch.float64, device="cuda")
+    ctx.pa_diag_E(dE)
+    assert rel_err(dE.cpu().numpy().reshape(sp.ne, -1) - 1.0, orc.pa_diag_E(A.qd, osp.basis)) < TOL_OP
     ctx.jacobi_setup()
     ctx.jacobi_dinv(dg)
     assert rel_err(dg.cpu().numpy(), orc.jacobi_dinv(A, osp.ess)) < TOL_OP
     ctx.close()
 
 
-@pytest.mark.parametrize("p,variant", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (5, 1), (5, 2), (6, 1), (6, 2), (7, 1), (8, 1)]
-                         + [(p, v) for p in range(1, 9) for v in (30, 31)] + [(4, 32), (5, 32), (6, 32), (7, 32)])
+@pytest.mark.parametrize("p,variant", [(p, v) for p in range(1, 9) for v in (20, 30, 31)] + [(4, 32), (7, 32)])
 def test_apply_kernel_alternative_variants(lpf, orc, cuda, p, variant):
     """The non-default (elements per CTA, CTAs per SM) instantiations of the persistent kernel, forced through
     several batches per CTA."""
@@ -93,7 +96,7 @@ def test_apply_kernel_alternative_variants(lpf, orc, cuda, p, variant):
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 10, 12, 14, 15, 20, 30, 31, 32, 100, 101, 102, 103, 104])
+@pytest.mark.parametrize("variant", [0, 20, 30, 31, 32])
 def test_apply_kernel_variants_p4(lpf, orc, cuda, variant):
     """Every compiled (elements-per-CTA, pipelining) variant of the order-4 kernel, on a mesh whose element
     count (7x1x3 refined once = 168, perturbed) is ragged for every batch size and spans several batches
@@ -352,7 +355,7 @@ def test_cylinder_rhs_third_weight_and_envelope(lpf, orc, cuda):
     ctx.close()
 
 
-@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("p", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 def test_affine_fast_path(lpf, orc, cuda, tank, p):
     """Affine hexes: D(q) = w_q * (detJ J^-1 J^-T) from one 6-entry tensor per element instead of stored q-data.
     Same operator to 1e-12, same solve; switched off automatically on a non-affine mesh."""

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(lpf):
     for name in sorted(declared):
         assert hasattr(lpf.lib, name), f"liblpf_b200.so does not export {name}"
     assert declared == set(lpf.SIGNATURES), declared ^ set(lpf.SIGNATURES)
-    assert lpf.lib.lpf_version() == 100
+    assert lpf.lib.lpf_version() == 200
 
 
 def test_error_reporting_without_aborting(lpf):
@@ -37,7 +37,7 @@ def test_error_reporting_without_aborting(lpf):
         lpf.Mesh.wave_tank(2, 1, 1, periodic_x=True)
     m = lpf.Mesh.wave_tank(3, 1, 1)
     with pytest.raises(lpf.LpfError, match="order"):
-        lpf.Space(m, 9)
+        lpf.Space(m, 11)
     with pytest.raises(lpf.LpfError):
         lpf.Space(m, 2, nranks=2, rank=5)
 
@@ -52,7 +52,7 @@ def test_device_entry_points_fail_loudly_without_gpu(lpf):
 
 
 def test_basis_tables_match_oracle(lpf, orc):
-    for p in range(1, 9):
+    for p in range(1, 11):
         t = lpf.basis_tables(p)
         bs = orc.make_basis(p)
         for k, ref in (("nodes", bs.nodes), ("qpts", bs.qpts), ("qwts", bs.qwts), ("B", bs.B), ("G", bs.G), ("Dhat", bs.Dhat)):

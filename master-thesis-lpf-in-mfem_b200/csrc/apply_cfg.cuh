@@ -69,9 +69,14 @@ struct __align__(16) LpfOrderTab {
 };
 
 #ifdef LPF_ORDER
-// two slots: the kernels address slot (it >> 30) with `it` the batch counter -- always slot 0, but loop-variant, which
-// keeps the compiler from hoisting all coefficients out of the batch loop (pa_apply_tma.cuh)
-static __constant__ LpfOrderTab<LPF_ORDER> c_ot[2];
+// Identical copies of the table.  The kernels address copy `s + z` where z is a loop-variant value that is always zero
+// (the batch counter >> 30, or a dedicated loop-carried variable): without it the compiler hoists all coefficients out of
+// the batch loop, overflows the uniform register file and shuffles them back with R2UR / MOV (pa_apply_tma.cuh).  With
+// TABS = 1 (orders >= 7) every stage s = 0..5 reads its own copy, so the coefficient loads of different stages cannot be
+// merged into values that stay live across the whole batch (that is what pushed orders 7, 8 to 250 registers and
+// per-thread LDC loads, profiles/r02_sass_opcodes.md).
+#define LPF_TAB_COPIES 7
+static __constant__ LpfOrderTab<LPF_ORDER> c_ot[LPF_TAB_COPIES];
 #endif
 
 // ---- TMA 1-D bulk copies + mbarriers ---------------------------------------------------------------------------------

@@ -18,21 +18,31 @@ namespace {
 
 constexpr int P = LPF_ORDER;
 
-template <int E, int MINB, bool EO, bool AFF = false, bool DET = false>
+// TABS < 0: the order's default (one coefficient-table copy per stage from order 7 up, from order 6 up in the kernels that
+// carry the overlapped halo exchange -- the variants where ptxas otherwise falls back to per-thread LDC loads,
+// profiles/r02_sass_opcodes.md)
+template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1>
 int launch_persistent(LpfApplyArgs &a)
 {
     using C = TmaCfg<P, E, AFF>;
+    constexpr int TS = TABS >= 0 ? TABS : (P >= 7 ? 1 : 0), TSO = TABS >= 0 ? TABS : (P >= 6 ? 1 : 0);
     static int blocks_per_sm[16] = {0};
-    void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs);
-    if constexpr (EO) { kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET>; }
-    else { kd = pa_apply_tma_kernel<P, E, true, MINB, DET>; kn = pa_apply_tma_kernel<P, E, false, MINB, DET>; }
+    void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs), (*kod)(const ApplyKArgs), (*kon)(const ApplyKArgs);
+    if constexpr (EO) {
+        kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, false, TS>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, false, TS>;
+        kod = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, true, TSO>; kon = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, true, TSO>;
+    } else {
+        kd = pa_apply_tma_kernel<P, E, true, MINB, DET, false>; kn = pa_apply_tma_kernel<P, E, false, MINB, DET, false>;
+        kod = pa_apply_tma_kernel<P, E, true, MINB, DET, true>; kon = pa_apply_tma_kernel<P, E, false, MINB, DET, true>;
+    }
     int &bps = blocks_per_sm[a.dev & 15];
     if (bps == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(kn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kd, C::NT, C::SMEM_BYTES));
-        if (bps < 1) bps = 1;
-        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, C::NT, (size_t)C::SMEM_BYTES, bps);
+        for (auto k : {kd, kn, kod, kon}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        int b0 = 0, b1 = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, kd, C::NT, C::SMEM_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, kod, C::NT, C::SMEM_BYTES));
+        bps = std::max(1, std::min(b0, b1));
+        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, C::NT, (size_t)C::SMEM_BYTES, bps);
     }
     const int nb = (a.k.ne + E - 1) / E;
     a.threads = C::NT; a.smem = C::SMEM_BYTES; a.grid = 0;
@@ -40,14 +50,15 @@ int launch_persistent(LpfApplyArgs &a)
     int grid = std::min(nb, a.max_ctas > 0 ? a.max_ctas : bps * a.sm_count);
     grid = std::min(grid, LPF_DEN_SLOTS);            // one (d, A d) slot per CTA
     a.grid = grid;
+    const bool ovl = a.k.tail.mode != 0;             // multi-GPU: the halo-sum rides on this launch
     if (a.k.tail.mode == 2) a.k.tail.n_if_batches = (a.k.tail.n_if_batches + E - 1) / E;     // elements -> batches
-    CUDA_TRY(launch_ex(a.pdl, a.k.den_slots ? kd : kn, dim3(grid), dim3(C::NT), C::SMEM_BYTES, a.stream, a.k));
+    CUDA_TRY(launch_ex(a.pdl, a.k.den_slots ? (ovl ? kod : kd) : (ovl ? kon : kn), dim3(grid), dim3(C::NT), C::SMEM_BYTES, a.stream, a.k));
     CUDA_TRY(cudaGetLastError());
     return LPF_OK;
 }
 
-// (E, CTAs/SM) of the tuned kernels, profiles/r01_sweep_orders.txt and r02 sweeps.  Even-odd contractions from order 3
-// up, plain contractions below; the affine fast path always uses the even-odd kernel.
+// (E, CTAs/SM) of the tuned kernels, profiles/r02_sweep_orders.txt.  Even-odd contractions from order 3 up, plain
+// contractions below; the affine fast path always uses the even-odd kernel.
 template <bool AFF, bool DET>
 int launch_default(LpfApplyArgs &a)
 {
@@ -89,15 +100,25 @@ int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
         else if constexpr (P <= 8) return launch_persistent<2, 1, false>(a);
         else return launch_persistent<1, 1, false>(a);
     }
-    if (v >= 30 && v < 40) {      // even-odd contractions, alternative (E, CTAs/SM) pairs for the tuning sweep
+    if (v >= 30 && v < 40) {      // even-odd contractions: alternative (E, CTAs/SM, table copies) for the tuning sweep
         if constexpr (P == 1) { if (v == 31) return launch_persistent<32, 2, true>(a); return launch_persistent<16, 3, true>(a); }
         else if constexpr (P == 2) { if (v == 31) return launch_persistent<16, 2, true>(a); return launch_persistent<8, 3, true>(a); }
         else if constexpr (P == 3) { if (v == 31) return launch_persistent<5, 4, true>(a); return launch_persistent<5, 3, true>(a); }
         else if constexpr (P == 4) { if (v == 31) return launch_persistent<4, 3, true>(a); if (v == 32) return launch_persistent<2, 5, true>(a); return launch_persistent<3, 4, true>(a); }
-        else if constexpr (P == 5) { if (v == 31) return launch_persistent<2, 4, true>(a); return launch_persistent<2, 3, true>(a); }
-        else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); return launch_persistent<2, 3, true>(a); }
-        else if constexpr (P == 7) { if (v == 31) return launch_persistent<2, 2, true>(a); if (v == 32) return launch_persistent<1, 3, true>(a); return launch_persistent<2, 1, true>(a); }
-        else if constexpr (P == 8) { if (v == 31) return launch_persistent<2, 1, true>(a); return launch_persistent<1, 2, true>(a); }
+        else if constexpr (P == 5) { if (v == 31) return launch_persistent<2, 4, true>(a); if (v == 32) return launch_persistent<3, 2, true, false, false, 1>(a); return launch_persistent<2, 3, true>(a); }
+        else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); if (v == 32) return launch_persistent<2, 2, true, false, false, 1>(a); return launch_persistent<2, 3, true>(a); }
+        else if constexpr (P == 7) {
+            if (v == 31) return launch_persistent<2, 2, true>(a);
+            if (v == 32) return launch_persistent<1, 3, true>(a);
+            if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a);      // the round-1 kernel (per-thread LDC)
+            if (v == 34) return launch_persistent<1, 3, true, false, false, 0>(a);
+            return launch_persistent<2, 1, true>(a);
+        }
+        else if constexpr (P == 8) {
+            if (v == 31) return launch_persistent<2, 1, true>(a);
+            if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a);      // the round-1 kernel (per-thread LDC)
+            return launch_persistent<1, 2, true>(a);
+        }
         else return launch_default<false, false>(a);
     }
     lpf::set_error("unknown apply_variant " + std::to_string(v));
@@ -129,7 +150,7 @@ int LPF_CAT(lpf_apply_E_p, LPF_ORDER)(const double *qd, const double *xE, double
 int LPF_CAT(lpf_apply_tables_p, LPF_ORDER)(const double *B, const double *G, const double *qwts)
 {
     constexpr int D = P + 1, Q = P + 2, DC = (D + 1) / 2, DH = D / 2, QC = (Q + 1) / 2, QH = Q / 2;
-    std::vector<LpfOrderTab<P>> tabs(2);
+    std::vector<LpfOrderTab<P>> tabs(LPF_TAB_COPIES);
     LpfOrderTab<P> &t = tabs[0];
     std::memset(&t, 0, sizeof(t));
     auto Bm = [&](int q, int d) { return B[(size_t)q * D + d]; };
@@ -156,7 +177,7 @@ int LPF_CAT(lpf_apply_tables_p, LPF_ORDER)(const double *B, const double *G, con
             t.GoT[d * QH + q] = 0.5 * (Gm(q, d) - Gm(Q - 1 - q, d));
         }
     }
-    tabs[1] = tabs[0];
-    CUDA_TRY(cudaMemcpyToSymbol(c_ot, tabs.data(), 2 * sizeof(LpfOrderTab<P>)));
+    for (int i = 1; i < LPF_TAB_COPIES; i++) tabs[i] = tabs[0];
+    CUDA_TRY(cudaMemcpyToSymbol(c_ot, tabs.data(), LPF_TAB_COPIES * sizeof(LpfOrderTab<P>)));
     return LPF_OK;
 }

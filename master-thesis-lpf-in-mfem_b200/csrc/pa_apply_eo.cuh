@@ -54,7 +54,7 @@ __device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N +
 // 87 % of the kernel's HBM bytes at order 4 -- disappears and the kernel becomes FP64-issue-bound.  Used automatically
 // when every element of the mesh is affine (all wave tanks of the reference); reported separately from the graded
 // stored-q-data number.
-template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false>
+template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false, bool OVL = false, int TABS = 0>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
 pa_apply_eo_kernel(const ApplyKArgs ka)
 {
@@ -113,7 +113,7 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         return;
     }
     P2POverlap ov;
-    if (ka.tail.mode == 2) p2p_if_begin(ka.tail, ov);
+    if (OVL && ka.tail.mode == 2) p2p_if_begin(ka.tail, ov);
     double xs[D], xsn[D];
     double part = 0.0;
     mbar_wait(bar_i, 0);
@@ -123,8 +123,8 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         for (int i = 0; i < D; i++) { const int g = gi[i]; xs[i] = g >= 0 ? x[g] : 0.0; }
     }
 
-    uint32_t it = 0;
-    for (; b < nb; b += gridDim.x, it++) {
+    uint32_t it = 0, zoff = 0;     // zoff: always zero, but only the loop knows (TABS)
+    for (; b < nb; b += gridDim.x, it++, zoff = (zoff + gridDim.x) >> 31) {
         const int e0 = b * E;
         const int bn = b + gridDim.x;
         const int e0n = bn * E;
@@ -135,8 +135,10 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         const bool xnext = xrole && has_next && (e0n + ex) < ne;
         const int cur = it & 1, nxt = cur ^ 1;
         // loop-variant (always zero) table offset: keeps the compiler from hoisting the coefficients out of the
-        // batch loop into (too few) uniform registers, see pa_apply_tma.cuh
-        const LpfOrderTab<P> &T = c_ot[it >> 30];
+        // batch loop into (too few) uniform registers, see pa_apply_tma.cuh; TABS: one table copy per stage (apply_cfg.cuh)
+        const uint32_t zv = TABS ? zoff : (it >> 30);
+        const LpfOrderTab<P> &T = c_ot[zv], &TY = c_ot[(TABS ? 1 : 0) + zv], &TZ = c_ot[(TABS ? 2 : 0) + zv],
+                             &TZb = c_ot[(TABS ? 3 : 0) + zv], &TYt = c_ot[(TABS ? 4 : 0) + zv], &TXt = c_ot[(TABS ? 5 : 0) + zv];
         double da[6];                                   // AFF: element tensor, loaded two stages before its use
         if (AFF && zvalid) {
             const double *de = qd + (size_t)(e0 + ez) * 6;
@@ -171,10 +173,10 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
             for (int i = 0; i < D; i++) { ua[i] = a[i * C::SAY]; ub[i] = a[C::SAA + i * C::SAY]; }
             double e[DC], o[DH], s0[Q], s1[Q], s2[Q];
             eo_split<D>(ua, e, o);
-            eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, s0);      // B_y B_x u
-            eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, s1);      // G_y B_x u
+            eo_contract<D, Q, +1, false>(TY.BeF, TY.BoF, e, o, s0);      // B_y B_x u
+            eo_contract<D, Q, -1, false>(TY.GeF, TY.GoF, e, o, s1);      // G_y B_x u
             eo_split<D>(ub, e, o);
-            eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, s2);      // B_y G_x u
+            eo_contract<D, Q, +1, false>(TY.BeF, TY.BoF, e, o, s2);      // B_y G_x u
             double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
 #pragma unroll
             for (int q = 0; q < Q; q++) { bb[q * Q] = s0[q]; bb[C::SBA + q * Q] = s1[q]; bb[2 * C::SBA + q * Q] = s2[q]; }
@@ -192,15 +194,15 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
 #pragma unroll
                 for (int i = 0; i < D; i++) u[i] = bb[2 * C::SBA + i * C::SBZ];       // G_x B_y u  -> B_z
                 eo_split<D>(u, e, o);
-                eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, g0);
+                eo_contract<D, Q, +1, false>(TZ.BeF, TZ.BoF, e, o, g0);
 #pragma unroll
                 for (int i = 0; i < D; i++) u[i] = bb[C::SBA + i * C::SBZ];           // B_x G_y u  -> B_z
                 eo_split<D>(u, e, o);
-                eo_contract<D, Q, +1, false>(T.BeF, T.BoF, e, o, g1);
+                eo_contract<D, Q, +1, false>(TZ.BeF, TZ.BoF, e, o, g1);
 #pragma unroll
                 for (int i = 0; i < D; i++) u[i] = bb[i * C::SBZ];                    // B_x B_y u  -> G_z
                 eo_split<D>(u, e, o);
-                eo_contract<D, Q, -1, false>(T.GeF, T.GoF, e, o, g2);
+                eo_contract<D, Q, -1, false>(TZ.GeF, TZ.GoF, e, o, g2);
             }
             if (AFF) {
                 const int qy = q2 / Q, qx = q2 - qy * Q;
@@ -226,15 +228,15 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
             {
                 double c[D], e[QC], o[QH];
                 eo_split<Q>(g0, e, o);
-                eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, c);
+                eo_contract<Q, D, +1, false>(TZb.BeT, TZb.BoT, e, o, c);
 #pragma unroll
                 for (int i = 0; i < D; i++) bb[2 * C::SBA + i * C::SBZ] = c[i];
                 eo_split<Q>(g1, e, o);
-                eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, c);
+                eo_contract<Q, D, +1, false>(TZb.BeT, TZb.BoT, e, o, c);
 #pragma unroll
                 for (int i = 0; i < D; i++) bb[C::SBA + i * C::SBZ] = c[i];
                 eo_split<Q>(g2, e, o);
-                eo_contract<Q, D, -1, false>(T.GeT, T.GoT, e, o, c);
+                eo_contract<Q, D, -1, false>(TZb.GeT, TZb.GoT, e, o, c);
 #pragma unroll
                 for (int i = 0; i < D; i++) bb[i * C::SBZ] = c[i];
             }
@@ -261,15 +263,15 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
 #pragma unroll
             for (int q = 0; q < Q; q++) v[q] = bb[q * Q];
             eo_split<Q>(v, e, o);
-            eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, ta);
+            eo_contract<Q, D, +1, false>(TYt.BeT, TYt.BoT, e, o, ta);
 #pragma unroll
             for (int q = 0; q < Q; q++) v[q] = bb[C::SBA + q * Q];
             eo_split<Q>(v, e, o);
-            eo_contract<Q, D, -1, true>(T.GeT, T.GoT, e, o, ta);
+            eo_contract<Q, D, -1, true>(TYt.GeT, TYt.GoT, e, o, ta);
 #pragma unroll
             for (int q = 0; q < Q; q++) v[q] = bb[2 * C::SBA + q * Q];
             eo_split<Q>(v, e, o);
-            eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, tb);
+            eo_contract<Q, D, +1, false>(TYt.BeT, TYt.BoT, e, o, tb);
             double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
 #pragma unroll
             for (int i = 0; i < D; i++) { a[i * C::SAY] = ta[i]; a[C::SAA + i * C::SAY] = tb[i]; }
@@ -284,11 +286,11 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
 #pragma unroll
             for (int q = 0; q < Q; q++) v[q] = a[q];
             eo_split<Q>(v, e, o);
-            eo_contract<Q, D, +1, false>(T.BeT, T.BoT, e, o, yv);
+            eo_contract<Q, D, +1, false>(TXt.BeT, TXt.BoT, e, o, yv);
 #pragma unroll
             for (int q = 0; q < Q; q++) v[q] = a[C::SAA + q];
             eo_split<Q>(v, e, o);
-            eo_contract<Q, D, -1, true>(T.GeT, T.GoT, e, o, yv);
+            eo_contract<Q, D, -1, true>(TXt.GeT, TXt.GoT, e, o, yv);
 #pragma unroll
             for (int i = 0; i < D; i++) {
                 const int g = gi[i];
@@ -303,11 +305,11 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
 #pragma unroll
             for (int i = 0; i < D; i++) xs[i] = xsn[i];
         }
-        apply_batch_end(ka.tail, ov, b, y);
+        apply_batch_end<OVL>(ka.tail, ov, b, y);
     }
 
     if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots);
     // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, riding on this kernel
-    if (ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
-    else if (ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
+    if (OVL && ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
+    else if (OVL && ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
 }

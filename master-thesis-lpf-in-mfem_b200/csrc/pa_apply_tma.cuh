@@ -43,9 +43,10 @@ __device__ __forceinline__ void apply_den_epilogue(double part, double *__restri
 
 // end of one batch: the __syncthreads that frees the stage buffers for the next batch, plus (multi-GPU, overlapped halo
 // exchange) the bookkeeping of the interface batches
+template <bool OVL>
 __device__ __forceinline__ void apply_batch_end(const P2PTail &tail, P2POverlap &ov, int b, const double *__restrict__ y)
 {
-    if (tail.mode == 2) {
+    if (OVL && tail.mode == 2) {
         const bool ifb = b < tail.n_if_batches;
         if (ifb) __threadfence();
         __syncthreads();
@@ -56,7 +57,7 @@ __device__ __forceinline__ void apply_batch_end(const P2PTail &tail, P2POverlap 
     }
 }
 
-template <int P, int E, bool DEN, int MINB, bool DET = false>
+template <int P, int E, bool DEN, int MINB, bool DET = false, bool OVL = false>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
 pa_apply_tma_kernel(const ApplyKArgs ka)
 {
@@ -114,7 +115,7 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
         return;
     }
     P2POverlap ov;
-    if (ka.tail.mode == 2) p2p_if_begin(ka.tail, ov);
+    if (OVL && ka.tail.mode == 2) p2p_if_begin(ka.tail, ov);
     double xs[D], xsn[D];
     double part = 0.0;
     mbar_wait(bar_i, 0);
@@ -289,12 +290,12 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
 #pragma unroll
             for (int i = 0; i < D; i++) xs[i] = xsn[i];
         }
-        apply_batch_end(ka.tail, ov, b, y);     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
+        apply_batch_end<OVL>(ka.tail, ov, b, y);     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
 #undef BGL
     }
 
     if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots);
     // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, riding on this kernel
-    if (ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
-    else if (ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
+    if (OVL && ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
+    else if (OVL && ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
 }

@@ -336,3 +336,25 @@ def test_surface_vtu_writer(lpf, tmp_path):
         pd = {d.get("Name"): np.array(d.text.split(), dtype=float) for d in piece.findall("PointData/DataArray")}
         # periodic field sampled at the cell's own coordinates
         assert np.allclose(pd["eta"], np.cos(2 * np.pi * pts[:, 0])) and np.allclose(pd["phi_fs"], 2 * pd["eta"])
+
+
+@pytest.mark.parametrize("family", ["tank_r2_p3", "finite_r1_p5", "big8_p2", "cylinder_p3"])
+def test_geometric_dof_map_between_product_and_oracle_numberings(lpf, orc, family):
+    """tests/util.py dof_map relates the product's numbering to the oracle's by geometry alone; it must be a bijection that
+    maps essential dofs onto essential dofs and surface dofs onto surface dofs on every mesh family of BASELINE.json."""
+    from util import dof_map, surface_map
+    H0 = 1.0 / (2.0 * np.pi)
+    cyl = os.path.join(os.path.dirname(os.path.abspath(__file__)), "meshes", "cylinder_half.mesh")
+    mk = {"tank_r2_p3": (lambda: lpf.Mesh.wave_tank(3, 1, 1).refine(2), lambda: orc.uniform_refine(orc.uniform_refine(orc.make_wave_tank(3, 1, 1, 1.0, 0.1, H0, True))), 3),
+          "finite_r1_p5": (lambda: lpf.Mesh.wave_tank(36, 1, 1, 12.0, 1.0, H0, False).refine(1), lambda: orc.uniform_refine(orc.make_wave_tank(36, 1, 1, 12.0, 1.0, H0, False)), 5),
+          "big8_p2": (lambda: lpf.Mesh.wave_tank(128, 2, 16), lambda: orc.make_wave_tank(128, 2, 16, 1.0, 0.1, H0, True), 2),
+          "cylinder_p3": (lambda: lpf.Mesh.read(cyl), lambda: orc.read_mfem_mesh(cyl), 3)}[family]
+    sp, osp = lpf.Space(mk[0](), mk[2]), orc.build_h1_space(mk[1](), mk[2])
+    pm = dof_map(sp, osp)
+    sm = surface_map(sp, osp, pm)
+    assert set(pm[sp.ess].tolist()) == set(osp.ess.tolist())
+    # same physical points (x compared on the circle: a seam dof of the x-periodic tanks may be represented by x = 0 or x = Lx)
+    Lx = osp.mesh.bounding_box()[1][0] - osp.mesh.bounding_box()[0][0]
+    a, b = sp.surf_xy, osp.surf_xy[sm][:, :2]
+    assert np.abs(a[:, 1] - b[:, 1]).max() < 1e-12
+    assert np.abs(np.exp(2j * np.pi * a[:, 0] / Lx) - np.exp(2j * np.pi * b[:, 0] / Lx)).max() < 1e-10

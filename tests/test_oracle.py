@@ -159,3 +159,29 @@ def test_golden_regression(orc):
     assert rel_err(orc.ConstrainedOperator(A, s.ess).mult(g["x"]), g["yc"]) < 1e-13
     fa = orc.FAOperator(s)
     assert rel_err(fa.mult(g["x"]), g["y"]) < 1e-12
+
+
+def test_independent_oracle_pinned_on_config1(orc, corc):
+    """The config-scale GPU tests (test_gpu_config_parity.py) check against IndependentOracle = oracle mesh + oracle
+    numbering + oracle basis + C element kernels.  Pin it here, on the CPU: against the numpy PA operator, and against the
+    known answers of config 1 (laplace_solver.cpp on wave-tank.mesh r=2: SURVEY App. E iteration counts 68 / 105)."""
+    import math
+    from util import IndependentOracle, rel_err
+    H0 = 1.0 / (2.0 * np.pi)
+    for p, its, err in ((3, 68, 6.3e-7), (4, 105, 1.7e-8)):
+        m = orc.uniform_refine(orc.uniform_refine(orc.make_wave_tank(3, 1, 1, 1.0, 0.1, H0, True)))
+        o = IndependentOracle(orc, corc, m, p)
+        A = orc.PAOperator(o.sp)
+        x = orc.hash_noise(o.n)
+        assert rel_err(o.mult(x), A.mult(x)) < 1e-13 and rel_err(o.diag(), A.diag()) < 1e-13
+        lo, hi = m.bounding_box()
+        k = 2 * math.pi / (hi[0] - lo[0]); h = hi[2] - lo[2]; kh = k * h
+        cw = math.sqrt((9.81 / k) * math.tanh(kh))
+        phi = -0.5 * 0.005 * cw * np.cosh(k * (o.sp.xyz[:, 2] - hi[2] + h)) / math.sinh(kh) * np.sin(-k * o.sp.xyz[:, 0])
+        X, info = o.solve(phi, 1e-12, 500)
+        assert info.converged and info.iters == its
+        assert rel_err(X, phi) < err
+        w_ex = -0.5 * 0.005 * cw * k * np.sin(-k * o.sp.surf_xy[:, 0])
+        assert rel_err(o.surface_dz(X), w_ex) < {3: 2e-4, 4: 3e-6}[p]
+        # GetDerivative through the C oracle == the numpy restatement
+        assert rel_err(o.surface_dz(X), orc.get_derivative_z(o.sp, X, orc.surface_elements(o.sp))[o.sp.surf2vol]) < 1e-12

@@ -35,6 +35,7 @@ def main():
         sp = lpf.Space(meshes[r], p)
         ctx = lpf.Context(sp, device=0, stream=torch.cuda.current_stream().cuda_stream)
         ctx.pa_setup()
+        ctx.set_option("affine", 0)          # the general stored-q-data kernels
         x = torch.rand(sp.ndof, dtype=torch.float64, device="cuda") - 0.5
         y = torch.empty_like(x)
         D, Q = p + 1, p + 2
@@ -45,7 +46,7 @@ def main():
                 ctx.time_apply(x, y, 3)
                 ms_t, ms_k, _ = ctx.time_apply(x, y, a.reps)
             except lpf.LpfError as e:
-                print(f"p={p} v={v}: {e}")
+                print(f"p={p} v={v}: {e}", flush=True)
                 continue
             ms_t /= a.reps; ms_k /= a.reps
             row = dict(order=p, variant=v, refine=r, hexes=sp.ne, dofs=sp.ndof, kernel_ms=ms_k, apply_ms=ms_t,

@@ -10,7 +10,9 @@ A "step" is one constrained operator apply y = (P^T A P)_c x on the whole mesh (
 calls once per iteration).  Workload at N=1: wave-tank-big8 (128x2x16 hexes, x-periodic)
 uniformly refined twice, H1 order 4: 262 144 hexes, 17 369 088 dofs, 2.7 GB of q-data (>> 126 MB L2, so
 no L2 flush is needed between iterations).  N>1: weak scaling, the tank is N times longer (128 N cells in
-x) and is cut into N x-slabs, one per GPU, halo-summed over NCCL after every apply.
+x) and is cut into N x-slabs, one per GPU; the halo-sum rides on the element kernel (NVLink peer memory, own kernels).
+Extra objects on the line: pcg_per_rk4_step (weak), strong_scaling (same total mesh on every N), e2e_rk4 (host-API RK4 step),
+parity (N > 1: N ranks against 1 rank), cpu_baseline (C restatement of MFEM's CPU PA path on the host cores).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -47,8 +49,19 @@ def parse():
     return ap.parse_args()
 
 
-def workload_name(a):
-    return f"wave-tank-big8(128x2x16,x-periodic) r={a.refine} order={a.order}"
+def workload_name(a, world=1):
+    tank = "128x2x16" if world == 1 else f"{128 * world}x2x16"
+    return f"wave-tank-big8({tank},x-periodic) r={a.refine} order={a.order}"
+
+
+def config_dict(a, world):
+    """identical in both arms (`--impl ours` / `--impl reference`): it names the WORKLOAD, not the implementation"""
+    f, p = 2 ** a.refine, a.order
+    hexes = 128 * 2 * 16 * f ** 3
+    dofs = (128 * world * f * p) * (2 * f * p + 1) * (16 * f * p + 1)
+    return {"workload": workload_name(a, world), "hexes_per_gpu": hexes, "dofs_global": dofs, "order": p,
+            "l2_policy": "inputs larger than L2 (q-data %.2f GB per GPU), no flush" % (hexes * 48 * (p + 2) ** 3 / 1e9),
+            "parallelism": f"x-slab domain decomposition x{world}, one slab per GPU" if world > 1 else "single GPU"}
 
 
 def algorithmic_bytes(ne, ndof, p):
@@ -106,69 +119,55 @@ def ncu_traffic(p, ne):
 
 
 # ------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the C restatement of MFEM's CPU PA path on the host cores
+# reference arm / cpu baseline: the C restatement of MFEM's CPU PA path on the host cores.  Mesh, numbering, basis tables
+# and arithmetic all come from oracle/ (oracle/cpu_reference.py); the product library is NOT loaded on this path.
 # ------------------------------------------------------------------------------------------------
-def cpu_apply_gdofs(order, refine, seconds=12.0, threads=None):
+def cpu_legs(a, steps, warmup, with_rk4=True):
+    """(cpu_baseline object, seconds per apply).  Apply: the SAME tank as the GPU arm's per-GPU workload (N = 1: the whole
+    workload).  PCG: one full RK4 step (4 Jacobi-PCG solves to rel 1e-12) on the tank of the GPU arm's RK4 leg."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_c                                 # checker / baseline only
-    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
-    nthreads = threads or os.cpu_count()
-    oracle_c.set_threads(nthreads)
-    sp = lpf.Space(lpf.Mesh.wave_tank(128, 2, 16).refine(refine), order)
-    cop = oracle_c.COperator(order, sp.corners, sp.gather, sp.ndof, lpf.basis_tables(order))
-    x = np.random.default_rng(0).random(sp.ndof) - 0.5
-    cop.mult_n(x, 1)
-    n, t0, chunk = 0, time.perf_counter(), 4       # work buffers are allocated once per chunk of applies (as in MFEM)
-    while True:
-        cop.mult_n(x, chunk)
-        n += chunk
-        el = time.perf_counter() - t0
-        if el > seconds and n >= 2:
-            break
-        chunk = min(64, chunk * 2)
-    return sp.ndof * n / el / 1e9, nthreads, f"{n} applies on wave-tank-big8 r={refine} order={order} ({sp.ne} hexes, {sp.ndof} dofs)", el / n
-
-
-def cpu_pcg_ms_per_iteration(order, refine, iters=40, threads=None):
-    """Second half of the metric on the CPU: the C restatement's Jacobi-PCG (same loop and stopping rule) on the tank of the
-    GPU's RK4 leg, capped at `iters` iterations (a bounded sample: a full RK4 step is 4 x 374 of them)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_c                                 # checker / baseline only
-    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
-    oracle_c.set_threads(threads or os.cpu_count())
-    sp = lpf.Space(lpf.Mesh.wave_tank(128, 2, 16).refine(refine), order)
-    cop = oracle_c.COperator(order, sp.corners, sp.gather, sp.ndof, lpf.basis_tables(order))
-    dinv = 1.0 / cop.diag()
-    dinv[sp.ess] = 1.0
-    x = np.zeros(sp.ndof)
-    x[sp.surf2vol] = np.cos(2 * np.pi * sp.surf_xy[:, 0])
-    t0 = time.perf_counter()
-    _, info = cop.pcg(np.sort(sp.ess), dinv, x, 1e-12, 0.0, iters)
-    el = time.perf_counter() - t0
-    return 1e3 * el / max(1, info["applies"] - 1), info["iterations"]
+    import cpu_reference as cr                      # baseline only
+    f = 2 ** a.refine
+    tk = cr.CpuTank(128 * f, 2 * f, 16 * f, a.order)
+    sec = tk.time_applies(steps, warmup)
+    out = {"value": tk.ndof / sec / 1e9, "unit": UNIT, "cores": tk.threads, "kind": "port",
+           "sample": f"{steps} applies (+{warmup} warm-up) on wave-tank-big8 r={a.refine} order={a.order}: {tk.describe()}"
+                     + (f" = one of the {a.gpus} x-slabs of the workload" if a.gpus > 1 else " = the whole workload"),
+           "ms_per_apply": sec * 1e3,
+           "what": "C/OpenMP restatement of MFEM's CPU partial-assembly path (oracle/pa_oracle.c, -march=native); MFEM/hypre/MPI are not installable here"}
+    del tk
+    if with_rk4:
+        try:
+            f1 = 2 ** a.rk4_refine
+            t1 = cr.CpuTank(128 * f1, 2 * f1, 16 * f1, a.order)
+            wv = cr.orc.Wave()
+            sec_rk4, its = t1.time_rk4_step(wv.T / 150, 1e-12, 2000)
+            out["rk4_ms_per_step"] = sec_rk4 * 1e3
+            out["pcg_ms_per_cg_iteration"] = sec_rk4 * 1e3 / max(1, sum(its))
+            out["rk4_cg_iterations_per_stage"] = its
+            out["rk4_sample"] = f"one full RK4 step (dt = T/150, 4 Jacobi-PCG solves, rel 1e-12) on wave-tank-big8 r={a.rk4_refine} order={a.order}: {t1.describe()}"
+        except Exception as e:                      # the baseline must never take the other numbers down with it
+            out["rk4_error"] = str(e)[:200]
+    return out, sec
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, a.steps)
-    ref = min(a.refine, 1)
-    # each "step" of the reference arm is a bounded sample: one apply on the r<=1 tank
-    g, nth, sample, sec = cpu_apply_gdofs(a.order, ref, seconds=min(60.0, 1.5 * (steps + a.warmup)))
-    line = {"impl": "reference", "metric": METRIC, "value": g, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+    steps, warmup = max(1, a.steps), max(1, a.warmup)
+    cb, sec = cpu_legs(a, steps, warmup, with_rk4=not a.no_rk4)
+    # whole-job value: throughput is per host, the workload is N times one slab -- the host needs N times as long
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": sec * 1e3 * a.gpus, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sample": sample},
-            "cpu_baseline": {"value": g, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample},
-            "e2e": {"value": g, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "MFEM/hypre/MPI are not installable here; this is the C/OpenMP restatement of MFEM's CPU PA path (oracle/pa_oracle.c)"}
-    try:
-        ms_it, nit = cpu_pcg_ms_per_iteration(a.order, a.rk4_refine)
-        line["cpu_baseline"]["pcg_ms_per_cg_iteration"] = ms_it
-        line["cpu_baseline"]["pcg_sample"] = f"{nit} Jacobi-PCG iterations on wave-tank-big8 r={a.rk4_refine} order={a.order}"
-    except Exception as e:
-        line["cpu_baseline"]["pcg_error"] = str(e)[:200]
+            "config": config_dict(a, a.gpus),
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    if "rk4_ms_per_step" in cb:
+        line["e2e_rk4"] = {"value": cb["rk4_ms_per_step"], "unit": "ms per RK4 step", "higher_is_better": False,
+                           "workload": cb["rk4_sample"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -286,10 +285,32 @@ def run_ours(a):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
-    # PCG time per RK4 step (strongscaling.cpp-like protocol: rel 1e-12, RK4, dt = T/150) on the r=1 tank
-    rk = None
+    # per-rank spread of the element kernel (which rank limits the weak-scaling number, and by how much)
+    kernel_ranks = [ms_k / a.steps]
+    if world > 1:
+        allk = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(allk, torch.tensor([ms_k / a.steps], dtype=torch.float64, device="cuda"))
+        kernel_ranks = [float(t[0]) for t in allk]
+
+    # PCG time per RK4 step (strongscaling.cpp-like protocol: rel 1e-12, RK4, dt = T/150) on the r=1 tank, weak-scaled
+    rk = strong = None
     if not a.no_rk4:
-        rk = rk4_measure(lpf, torch, a, local, stream, world, rank, dist if world > 1 else None)
+        rk = rk4_measure(lpf, torch, a, local, stream, world, rank, dist if world > 1 else None, weak=True, refine=a.rk4_refine)
+        # STRONG scaling (strongscaling.cpp:119-125 protocol): the same total mesh on every N -- big8 once refined
+        # (2.25 M dofs) and big8 itself (299 520 dofs, the config the north star names), cut into N x-slabs
+        strong = {}
+        for name, r in (("big8_r1", 1), ("big8", 0)):
+            m = rk4_measure(lpf, torch, a, local, stream, world, rank, dist if world > 1 else None, weak=False, refine=r, affine_leg=False)
+            strong[name] = {k: m[k] for k in ("workload", "ms_per_rk4_step", "ms_per_cg_iteration", "cg_iterations_per_stage", "gpu_launches_per_step")}
+
+    # multi-GPU correctness carried by the bench line itself: a small tank solved on N ranks against the single-rank run
+    parity = None
+    if world > 1:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import check_multi_gpu
+        res, fails = check_multi_gpu.run_checks(lpf, world, rank, local, stream, comm=a.comm, order=p, mesh_kind="tank", verbose=False)
+        parity = {"mesh": "wave tank 32x2x8, perturbed, order %d, %d ranks vs 1 rank (same library; tests/ pin the 1-rank run against the oracle)" % (p, world),
+                  "ok": not fails, "failed": fails, **{k.replace(" ", "_"): v for k, v in res.items()}}
 
     if rank != 0:
         if world > 1:
@@ -299,17 +320,19 @@ def run_ours(a):
     peak, peak_src = measured_peak()
     ab = algorithmic_bytes(sp.ne, sp.ndof, p)
     achieved = ab / (ms_kernel * 1e-3) / 1e9
+    cfg = config_dict(a, world)
+    assert cfg["hexes_per_gpu"] == sp.ne and cfg["dofs_global"] == ndof_global, (cfg, sp.ne, ndof_global)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(3, a.warmup),
         "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "hexes_per_gpu": sp.ne, "dofs_global": ndof_global, "order": p,
-                   "l2_policy": "inputs larger than L2 (q-data %.2f GB per GPU), no flush" % (sp.ne * 48 * (p + 2) ** 3 / 1e9),
-                   "parallelism": (f"x-slab domain decomposition x{world}, halo-sum over " + ("NVLink peer memory (own kernels)" if a.comm == "p2p" else "NCCL send/recv")) if world > 1 else "single GPU",
-                   "apply_variant": a.variant},
+        "config": cfg,
+        "exchange": (("halo-sum inside the apply kernel over NVLink peer memory (own kernels), overlapped with interior elements" if a.comm == "p2p" else "NCCL send/recv + all-reduce") if world > 1 else None),
+        "apply_variant": a.variant,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(p, sp.ne), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
-                     "kernel_ms": ms_kernel, "kernel": "pa_apply_eo_kernel" if p >= 3 else "pa_apply_tma_kernel"},
+                     "kernel_ms": ms_kernel, "kernel_ms_per_rank": {"min": min(kernel_ranks), "median": float(np.median(kernel_ranks)), "max": max(kernel_ranks)},
+                     "kernel": "pa_apply_eo_kernel" if p >= 3 else "pa_apply_tma_kernel"},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "steps": e2e_steps, "api": "lpf_apply_T_host (pinned host x -> device -> apply -> host y)"},
         "gpu_launches": int(launches),
@@ -319,25 +342,25 @@ def run_ours(a):
         line["affine_fastpath"] = aff
     if rk is not None:
         line["pcg_per_rk4_step"] = rk
+        line["strong_scaling"] = strong
+        line["e2e_rk4"] = {"value": rk["ms_per_rk4_step_host_api"], "unit": "ms per RK4 step", "higher_is_better": False,
+                           "workload": rk["workload"], "api": "lpf_rk4_step_host (host state -> device, 4 Laplace solves + surface work, -> host)",
+                           "h2d_bytes_per_step": rk["h2d_d2h_bytes_per_step"] // 2, "d2h_bytes_per_step": rk["h2d_d2h_bytes_per_step"] // 2}
+    if parity is not None:
+        line["parity"] = parity
     if not a.no_cpu:
-        g, nth, sample, _ = cpu_apply_gdofs(p, min(a.refine, 1), seconds=12.0)
-        line["cpu_baseline"] = {"value": g, "unit": UNIT, "cores": nth, "kind": "port", "sample": sample}
-        try:
-            ms_it, nit = cpu_pcg_ms_per_iteration(p, a.rk4_refine)
-            line["cpu_baseline"]["pcg_ms_per_cg_iteration"] = ms_it
-            line["cpu_baseline"]["pcg_sample"] = f"{nit} Jacobi-PCG iterations on wave-tank-big8 r={a.rk4_refine} order={p} (the RK4 leg's mesh; a step is 4 solves)"
-        except Exception as e:                      # the baseline must never take the GPU numbers down with it
-            line["cpu_baseline"]["pcg_error"] = str(e)[:200]
+        line["cpu_baseline"], _ = cpu_legs(a, max(3, min(a.steps, 10)), 2, with_rk4=not a.no_rk4)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def rk4_measure(lpf, torch, a, local, stream, world=1, rank=0, dist=None):
-    """PCG time per RK4 step: strongscaling.cpp protocol (rel 1e-12, dt = T/150, 1 warm-up step) on the r=1 tank; N>1 is
-    weak-scaled like the matvec (tank N times longer, one x-slab per GPU).  Device-event time, max over ranks."""
+def rk4_measure(lpf, torch, a, local, stream, world=1, rank=0, dist=None, weak=True, refine=1, affine_leg=True):
+    """PCG time per RK4 step: strongscaling.cpp protocol (rel 1e-12, dt = T/150, 1 warm-up step).  weak: the tank is N times
+    longer, one x-slab of 128 x 2 x 16 (refined) per GPU; strong: the SAME tank cut into N x-slabs.  Device-event time, max over ranks."""
     p = a.order
-    mesh = lpf.Mesh.wave_tank(128 * world, 2, 16, Lx=1.0 * world).refine(a.rk4_refine)
+    nxf = world if weak else 1
+    mesh = lpf.Mesh.wave_tank(128 * nxf, 2, 16, Lx=1.0 * nxf).refine(refine)
     sp = lpf.Space(mesh, p, nranks=world, rank=rank)
     ctx = lpf.Context(sp, device=local, stream=stream)
     if world > 1 and a.comm == "p2p":
@@ -390,14 +413,14 @@ def rk4_measure(lpf, torch, a, local, stream, world=1, rank=0, dist=None):
     th = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(th, op=dist.ReduceOp.MAX)
-    out = {"workload": f"wave-tank-big8 x{world} r={a.rk4_refine} order={p} ({sp.ne} hexes per GPU, {int(sp.n_true_global)} dofs), RK4 dt=T/150, Jacobi-PCG rel 1e-12",
+    out = {"workload": f"wave-tank-big8 x{nxf} r={refine} order={p} on {world} GPU(s) ({sp.ne} hexes on rank 0, {int(sp.n_true_global)} dofs), RK4 dt=T/150, Jacobi-PCG rel 1e-12",
            "ms_per_rk4_step": ms, "cg_iterations_per_stage": its, "converged": [int(i.converged) for i in infos],
            "ms_per_cg_iteration": ms / max(1, sum(its)), "gpu_launches_per_step": launches_per_step,
            "ms_per_rk4_step_host_api": float(th[0]), "h2d_d2h_bytes_per_step": int(16 * len(st))}
     # extra: the same steps with the affine fast path
     ctx.set_option("affine", 1)
-    if ctx.affine_active:
-        sd2 = torch.from_numpy(st).cuda()
+    if affine_leg and ctx.affine_active:
+        sd2 = torch.from_numpy(st).cuda() if len(st) else torch.zeros(2, dtype=torch.float64, device="cuda")
         t2 = ctx.rk4_step(sd2, 0.0, dt)
         barrier()
         ev0.record()

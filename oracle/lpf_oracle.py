@@ -463,6 +463,42 @@ def build_h1_space(mesh: HexMesh, p: int, ess_attr=2) -> H1Space:
     return sp_
 
 
+def build_tank_space(nx, ny, nz, Lx, Ly, H, p, periodic_x=True) -> H1Space:
+    """H1 space of the wave-tank generator's box mesh (Meshes/wave_tank.cpp:13-47, Meshes/wave-tank-finite.cpp:10-45) by
+    LATTICE numbering: dof (ix, iy, iz) of the (nx p [+1]) x (ny p + 1) x (nz p + 1) node lattice, x wrapped when
+    periodic.  Same dof identification as build_h1_space(make_wave_tank(...)) (tests/test_oracle.py checks that the two
+    numberings induce the same partition) at a cost linear in the mesh size -- this is what lets the CPU reference arm of
+    bench.py run the full 262 144-hex workload.  A uniformly refined tank IS the tank with 2^r times the cells."""
+    bs = make_basis(p)
+    D = bs.D
+    NX = nx * p if periodic_x else nx * p + 1
+    NY, NZ = ny * p + 1, nz * p + 1
+    ex, ey, ez = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing='ij')
+    ex, ey, ez = (a.transpose(2, 1, 0).reshape(-1) for a in (ex, ey, ez))          # element index: x fastest
+    i = np.arange(D)
+    gx = (ex[:, None] * p + i[None, :]) % NX if periodic_x else ex[:, None] * p + i[None, :]
+    gy = ey[:, None] * p + i[None, :]
+    gz = ez[:, None] * p + i[None, :]
+    gather = (gx[:, None, None, :] + NX * (gy[:, None, :, None] + NY * gz[:, :, None, None])).reshape(len(ex), D ** 3)
+    ndof = NX * NY * NZ
+    hx, hy, hz = Lx / nx, Ly / ny, H / nz
+    corners = np.zeros((len(ex), 8, 3))
+    for c in range(8):
+        corners[:, c, 0] = (ex + (c & 1)) * hx
+        corners[:, c, 1] = (ey + ((c >> 1) & 1)) * hy
+        corners[:, c, 2] = (ez + ((c >> 2) & 1)) * hz
+    mesh = HexMesh(elems=np.zeros((len(ex), 8), dtype=np.int64), corners=corners, bdr=np.zeros((0, 4), dtype=np.int64),
+                   bdr_attr=np.zeros(0, dtype=np.int64), nv=0)
+    nodes = bs.nodes
+    X1 = ((np.arange(nx)[:, None] + nodes[None, :p]).reshape(-1) * hx) if periodic_x else \
+        np.concatenate([(np.arange(nx)[:, None] + nodes[None, :p]).reshape(-1), [nx]]) * hx
+    Y1 = np.concatenate([(np.arange(ny)[:, None] + nodes[None, :p]).reshape(-1), [ny]]) * hy
+    Z1 = np.concatenate([(np.arange(nz)[:, None] + nodes[None, :p]).reshape(-1), [nz]]) * hz
+    xyz = np.stack([np.tile(X1, NY * NZ), np.tile(np.repeat(Y1, NX), NZ), np.repeat(Z1, NX * NY)], axis=1)
+    surf2vol = NX * NY * (NZ - 1) + np.arange(NX * NY, dtype=np.int64)             # top lattice plane = boundary attribute 2
+    return H1Space(p, bs, mesh, gather, ndof, xyz, surf2vol.copy(), surf2vol, xyz[surf2vol])
+
+
 def _face_local_dofs(f, D):
     idx = np.arange(D ** 3).reshape(D, D, D)   # [k][j][i]
     if f == 0: return idx[0, :, :].reshape(-1)

@@ -7,8 +7,30 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblpf_oracle.so")
-if not os.path.exists(_SO):
-    subprocess.check_call(["make", "-C", _HERE])
+
+
+def _cpu_sig():
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return hashlib.md5(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _built_for_this_cpu():
+    try:
+        return open(_SO + ".cpu").read().strip() == _cpu_sig()
+    except OSError:
+        return False
+
+
+# compiled -march=native: rebuild when missing or built on another CPU (the .so travels from the build container to the GPU box)
+if not os.path.exists(_SO) or not _built_for_this_cpu():
+    subprocess.check_call(["make", "-B", "-C", _HERE], stdout=subprocess.DEVNULL)
 lib = C.CDLL(_SO)
 _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
 lib.lpf_or_max_threads.restype = C.c_int

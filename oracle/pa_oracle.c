@@ -25,8 +25,8 @@
 #include <omp.h>
 #endif
 
-#define MAXD 9
-#define MAXQ 10
+#define MAXD 11
+#define MAXQ 12
 
 void lpf_or_set_threads(int n)
 {
@@ -118,9 +118,10 @@ apply_element(const int D, const int Q, const double *restrict B, const double *
               const double *restrict qd, const double *restrict u, double *restrict y)
 {
     const int Q3 = Q * Q * Q;
-    double bx[MAXD][MAXD][MAXQ], gx[MAXD][MAXD][MAXQ];
-    double bb[MAXD][MAXQ][MAXQ], gb[MAXD][MAXQ][MAXQ], bg[MAXD][MAXQ][MAXQ];
-    double f0[MAXQ][MAXQ][MAXQ], f1[MAXQ][MAXQ][MAXQ], f2[MAXQ][MAXQ][MAXQ];
+    /* D, Q are literal constants at every call site, so these are fixed-size arrays after inlining */
+    double bx[D][D][Q], gx[D][D][Q];
+    double bb[D][Q][Q], gb[D][Q][Q], bg[D][Q][Q];
+    double f0[Q][Q][Q], f1[Q][Q][Q], f2[Q][Q][Q];
     /* x contraction */
     for (int dz = 0; dz < D; dz++)
         for (int dy = 0; dy < D; dy++)
@@ -211,7 +212,7 @@ int lpf_or_apply_E(int ne, int p, const double *B, const double *G, const double
 {
     switch (p) {
         APPLY_CASE(1) APPLY_CASE(2) APPLY_CASE(3) APPLY_CASE(4)
-        APPLY_CASE(5) APPLY_CASE(6) APPLY_CASE(7) APPLY_CASE(8)
+        APPLY_CASE(5) APPLY_CASE(6) APPLY_CASE(7) APPLY_CASE(8) APPLY_CASE(9) APPLY_CASE(10)
         default: return -1;
     }
     return 0;

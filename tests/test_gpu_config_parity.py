@@ -74,14 +74,18 @@ class Pair:
         assert err_d < TOL_OP, f"diagonal: {err_d:.2e}"
         return err
 
-    def check_solve(self, phi_o, rel_tol, max_iter, its_tol=1):
+    def check_solve(self, phi_o, rel_tol, max_iter, its_tol=1, sol_tol=None):
+        """Laplace solve on both sides.  Converged potentials (rel 1e-12 solves) must agree to 1e-10; a solve stopped at a
+        looser tolerance (ws.cpp: 1e-8) is only defined up to that tolerance -- two runs whose counts differ by the
+        allowed +-1 differ by one CG update -- so it is compared at 10 x rel_tol."""
+        sol_tol = sol_tol if sol_tol is not None else max(TOL_SOL, 10.0 * rel_tol)
         pd = _dev(self.torch, self.to_product(phi_o))
         info = self.ctx.laplace_solve(pd, rel_tol=rel_tol, max_iter=max_iter)
         X, oi = self.o.solve(phi_o, rel_tol, max_iter)
         err = rel_err(pd.cpu().numpy(), self.to_product(X))
         assert info.converged == oi.converged
         assert abs(info.iterations - oi.iters) <= its_tol, (info.iterations, oi.iters)
-        assert err < TOL_SOL, f"potential: {err:.2e}"
+        assert err < sol_tol, f"potential: {err:.2e}"
         return info, oi, X, pd
 
     def close(self):
@@ -201,25 +205,26 @@ def test_c3_big8_p4_operator_and_solve(lpf, orc, big8, cuda):
     pr.ctx.jacobi_setup()
 
 
-def test_c3_big8_p4_rk4_step(lpf, orc, big8, cuda):
-    """one RK4 step of the ws.cpp physics (no relaxation zones, dt = T/10, rel 1e-8, <= 300 its) on big8, order 4"""
+@pytest.mark.parametrize("rel_tol,max_iter,tol_eta,tol_phi", [(1e-12, 1000, TOL_SOL, TOL_SOL), (1e-8, 300, 1e-5, 1e-7)])
+def test_c3_big8_p4_rk4_step(lpf, orc, big8, cuda, rel_tol, max_iter, tol_eta, tol_phi):
+    """one RK4 step of the ws.cpp physics (no relaxation zones, dt = T/10) on big8, order 4: with converged solves
+    (rel 1e-12) the state agrees to 1e-10; with ws.cpp's own solver settings (rel 1e-8, <= 300 its) the two sides stop at
+    iterates that differ by the solver tolerance, amplified in eta by d/dz -- compared at that level."""
     pr = big8
     wv = orc.Wave()
     osp = pr.o.sp
     dt = wv.T / 10
-    f = orc.RhsLinear(osp, wv, rel_tol=1e-8, max_iter=300, operator=pr.o)
+    f = orc.RhsLinear(osp, wv, rel_tol=rel_tol, max_iter=max_iter, operator=pr.o)
     st_o = np.concatenate([wv.eta(0.0, osp.surf_xy[:, 0], osp.surf_xy[:, 1]), wv.phi_fs(0.0, osp.surf_xy[:, 0], osp.surf_xy[:, 1])])
-    pr.ctx.rhs_setup(lpf.make_rhs_params(lpf.wave_params(), rel_tol=1e-8, max_iter=300))
+    pr.ctx.rhs_setup(lpf.make_rhs_params(lpf.wave_params(), rel_tol=rel_tol, max_iter=max_iter))
     ns = pr.sp.nsurf
     sd = _dev(cuda, st_o[np.concatenate([pr.sm, ns + pr.sm])])
     st_o, _ = orc.rk4_step(f, st_o, 0.0, dt)
     pr.ctx.rk4_step(sd, 0.0, dt)
     its_p = [i.iterations for i in pr.ctx.last_solve_info()]
     assert all(abs(a - b) <= 1 for a, b in zip(its_p, f.iters)), (its_p, f.iters)
-    # the solves stop at rel 1e-8, so the two states agree to the solver tolerance times the conditioning of w~ = d(phi)/dz,
-    # not to 1e-10; each side's own fixed point is compared at 1e-10 in the 1e-12 solves above and in C2
-    assert rel_err(sd.cpu().numpy()[:ns], st_o[:ns][pr.sm]) < 1e-6
-    assert rel_err(sd.cpu().numpy()[ns:], st_o[ns:][pr.sm]) < 1e-8
+    assert rel_err(sd.cpu().numpy()[:ns], st_o[:ns][pr.sm]) < tol_eta
+    assert rel_err(sd.cpu().numpy()[ns:], st_o[ns:][pr.sm]) < tol_phi
 
 
 # ---- C4 -----------------------------------------------------------------------------------------

@@ -25,53 +25,51 @@ def rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--order", type=int, default=4)
-    ap.add_argument("--mesh", default="tank")
-    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
-    a = ap.parse_args()
-    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
-    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    torch.cuda.set_stream(torch.cuda.Stream())
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream().cuda_stream
-    if a.mesh == "tank":
+def run_checks(lpf, world, rank, local, stream, comm="p2p", order=4, mesh_kind="tank", verbose=True, host_apply=True, options=None):
+    """N-rank results against the single-rank run of the same library on this rank's GPU (which tests/ pins against the
+    oracle).  Returns {check name: value} and the list of failed checks (identical on every rank).  `options`: extra
+    (name, value) pairs for lpf_set_option on the multi-rank context (e.g. p2p_fuse)."""
+    stream_ptr = stream
+    if mesh_kind == "tank":
         mesh = lpf.Mesh.wave_tank(32, 2, 8).perturb(0.1)
     else:
         mesh = lpf.Mesh.read(os.path.join(ROOT, "tests", "meshes", "cylinder_half.mesh"))
-    p = a.order
+    p = order
     sp = lpf.Space(mesh, p, nranks=world, rank=rank)
-    ctx = lpf.Context(sp, device=local, stream=stream)
-    if a.comm == "p2p":
-        ctx.p2p_connect(dist)                       # our own NVLink peer-memory exchange, no NCCL inside the solver
-    else:
-        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
-        dist.broadcast(idt, 0)
-        ctx.comm_init(idt.cpu().numpy().tobytes())
-    if rank == 0:
-        print(f"communication: {a.comm}", flush=True)
+    ctx = lpf.Context(sp, device=local, stream=stream_ptr)
+    for k, v in (options or []):
+        ctx.set_option(k, v)
+
+    def connect(c):
+        if comm == "p2p":
+            c.p2p_connect(dist)                       # our own NVLink peer-memory exchange, no NCCL inside the solver
+        else:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(idt, 0)
+            c.comm_init(idt.cpu().numpy().tobytes())
+
+    connect(ctx)
     ctx.pa_setup()
     ctx.jacobi_setup()
 
     # serial twin on this rank's GPU (every rank builds it: cheap at this size, and no gather of inputs needed)
     ssp = lpf.Space(mesh, p)
-    sctx = lpf.Context(ssp, device=local, stream=stream)
+    sctx = lpf.Context(ssp, device=local, stream=stream_ptr)
     sctx.pa_setup()
     sctx.jacobi_setup()
     l2g = torch.from_numpy(sp.l2g.astype(np.int64)).cuda()
-    fails = []
+    fails, results = [], {}
 
     def check(name, val, tol):
-        ok = val < tol
-        t = torch.tensor([0.0 if ok else 1.0], device="cuda")
-        dist.all_reduce(t)
-        if rank == 0:
-            print(f"  {name:34s} {val:.3e}  (tol {tol:g})  {'ok' if float(t[0]) == 0 else 'FAIL'}", flush=True)
-        if float(t[0]) != 0:
+        t = torch.tensor([float(val), 0.0 if val < tol else 1.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst, bad = float(t[0]), float(t[1]) != 0
+        results[name] = worst
+        if rank == 0 and verbose:
+            print(f"  {name:34s} {worst:.3e}  (tol {tol:g})  {'FAIL' if bad else 'ok'}", flush=True)
+        if bad:
             fails.append(name)
 
     gen = torch.Generator(device="cuda").manual_seed(7)
@@ -103,7 +101,8 @@ def main():
     mi = ctx.laplace_solve(pl, rel_tol=1e-12, max_iter=2000)
     check("laplace solve potential", rel(pl.cpu().numpy(), pg[l2g].cpu().numpy()), 1e-10)
     check("CG iterations |multi - single|", abs(mi.iterations - si.iterations), 1.5)
-    if rank == 0:
+    results["iterations_single"], results["iterations_multi"] = si.iterations, mi.iterations
+    if rank == 0 and verbose:
         print(f"    iterations: single {si.iterations}, {world} GPUs {mi.iterations}", flush=True)
 
     # three RK4 steps of the ss.cpp RHS
@@ -114,7 +113,7 @@ def main():
     sg = torch.from_numpy(st).cuda()
     sg_idx = torch.from_numpy(sp.surf_g.astype(np.int64)).cuda()
     ns_g, ns_l = ssp.nsurf, sp.nsurf
-    sl = torch.cat([sg[:ns_g][sg_idx], sg[ns_g:][sg_idx]]).contiguous()
+    sl = torch.cat([sg[:ns_g][sg_idx], sg[ns_g:][sg_idx]]).contiguous() if ns_l else torch.zeros(2, dtype=torch.float64, device="cuda")
     dt = w["T"] / 60
     tg = tl = 0.0
     for _ in range(3):
@@ -130,21 +129,15 @@ def main():
     check("RK4 stage CG iterations", max(abs(x - y) for x, y in zip(its_s, its_m)), 1.5)
     # host-buffer entry point on a mesh large enough for its pipelined path (H2D ranges / element chunks / D2H ranges,
     # ranges holding shared dofs leave after the halo-sum): must equal the device-resident apply of the same rank
-    if a.mesh == "tank":
+    if mesh_kind == "tank" and host_apply:
         big = lpf.Mesh.wave_tank(64 * world, 2, 16, Lx=1.0 * world).refine(1)
         bsp = lpf.Space(big, p, nranks=world, rank=rank)
-        bctx = lpf.Context(bsp, device=local, stream=stream)
-        if a.comm == "p2p":
-            bctx.p2p_connect(dist)
-        else:
-            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                idt = torch.frombuffer(bytearray(lpf.comm_unique_id()), dtype=torch.uint8).cuda()
-            dist.broadcast(idt, 0)
-            bctx.comm_init(idt.cpu().numpy().tobytes())
+        bctx = lpf.Context(bsp, device=local, stream=stream_ptr)
+        for k, v in (options or []):
+            bctx.set_option(k, v)
+        connect(bctx)
         bctx.pa_setup()
-        xb = torch.rand(bsp.ndof, dtype=torch.float64, device="cuda", generator=gen) - 0.5
-        # make the copies of shared dofs consistent across ranks (x is an L-vector): take the value keyed by global id
+        # x is an L-vector: copies of shared dofs must be consistent across ranks, so key the values by global id
         key = torch.from_numpy(bsp.l2g.astype(np.float64)).cuda()
         xb = torch.sin(key * 0.001) * 0.5
         yb = torch.empty_like(xb)
@@ -154,12 +147,33 @@ def main():
         bctx.apply_T_host(xh, yh)
         check(f"host apply, pipelined ({bsp.ndof} dofs/rank)", rel(yh.numpy(), yb.cpu().numpy()), 1e-12)
         bctx.close()
-    if rank == 0:
+    if rank == 0 and verbose:
         print(f"    stage iterations: single {its_s}, {world} GPUs {its_m}")
-        print("MULTI-GPU PARITY: " + ("OK" if not fails else "FAILED " + str(fails)), flush=True)
-    if a.comm == "p2p":
+    if comm == "p2p":
         check("p2p flag waits timed out", float(ctx.p2p_error()), 0.5)
     ctx.close(); sctx.close()
+    return results, fails
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--mesh", default="tank")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"])
+    ap.add_argument("--p2p-fuse", type=int, default=-1, help="option p2p_fuse of the multi-rank context (-1: library default)")
+    a = ap.parse_args()
+    lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    torch.cuda.set_stream(torch.cuda.Stream())
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream().cuda_stream
+    if rank == 0:
+        print(f"communication: {a.comm}, p2p_fuse {a.p2p_fuse}", flush=True)
+    opts = [("p2p_fuse", a.p2p_fuse)] if a.p2p_fuse >= 0 else None
+    _, fails = run_checks(lpf, world, rank, local, stream, a.comm, a.order, a.mesh, options=opts)
+    if rank == 0:
+        print("MULTI-GPU PARITY: " + ("OK" if not fails else "FAILED " + str(fails)), flush=True)
     dist.destroy_process_group()
     sys.exit(1 if fails else 0)
 

@@ -76,8 +76,9 @@ int launch_default(LpfApplyArgs &a)
         else if constexpr (P == 3) return launch_persistent<8, 2, true, false, DET>(a);
         else if constexpr (P == 4) return launch_persistent<3, 3, true, false, DET>(a);
         else if constexpr (P == 5) return launch_persistent<3, 2, true, false, DET>(a);
-        else if constexpr (P == 6) return launch_persistent<2, 2, true, false, DET>(a);
-        else if constexpr (P <= 8) return launch_persistent<1, 2, true, false, DET>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 3, true, false, DET>(a);
+        else if constexpr (P == 7) return launch_persistent<1, 3, true, false, DET>(a);
+        else if constexpr (P == 8) return launch_persistent<1, 2, true, false, DET>(a);
         else return launch_persistent<1, 1, true, false, DET>(a);
     }
 }
@@ -106,10 +107,10 @@ int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
         else if constexpr (P == 3) { if (v == 31) return launch_persistent<5, 4, true>(a); return launch_persistent<5, 3, true>(a); }
         else if constexpr (P == 4) { if (v == 31) return launch_persistent<4, 3, true>(a); if (v == 32) return launch_persistent<2, 5, true>(a); return launch_persistent<3, 4, true>(a); }
         else if constexpr (P == 5) { if (v == 31) return launch_persistent<2, 4, true>(a); if (v == 32) return launch_persistent<3, 2, true, false, false, 1>(a); return launch_persistent<2, 3, true>(a); }
-        else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); if (v == 32) return launch_persistent<2, 2, true, false, false, 1>(a); return launch_persistent<2, 3, true>(a); }
+        else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); if (v == 32) return launch_persistent<2, 2, true, false, false, 1>(a); return launch_persistent<2, 2, true>(a); }
         else if constexpr (P == 7) {
             if (v == 31) return launch_persistent<2, 2, true>(a);
-            if (v == 32) return launch_persistent<1, 3, true>(a);
+            if (v == 32) return launch_persistent<1, 2, true>(a);
             if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a);      // the round-1 kernel (per-thread LDC)
             if (v == 34) return launch_persistent<1, 3, true, false, false, 0>(a);
             return launch_persistent<2, 1, true>(a);

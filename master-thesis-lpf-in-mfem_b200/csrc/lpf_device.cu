@@ -122,7 +122,7 @@ struct lpf_ctx {
     // pipelined host entry point (lpf_apply_T_host): element chunks / dof ranges, copy streams, events
     int sub_e0 = 0, sub_ne = -1;               // element sub-range for the next apply launch (-1 = all)
     int host_pipeline = 1;                     // option
-    std::vector<int> hp_elem_end;              // [K] end element of chunk k
+    std::vector<int> hp_elem_begin, hp_elem_end; // [K] element range of chunk k
     std::vector<int> hp_x_ranges_needed;       // [K] number of leading dof ranges chunk k reads
     std::vector<std::vector<int>> hp_final;    // [K] dof ranges whose y is final once chunk k is done
     std::vector<int> hp_range_end, hp_ess_end; // [R] end dof of range j, end position in the (sorted) ess list
@@ -415,6 +415,14 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
             for (int k = 0; k < D3; k++) gp[(size_t)e * DP3 + k] = d->gather[(size_t)e * D3 + k];
         LPF_TRY(upload(c->gmap, gp.data(), gp.size(), &c->bytes));
     }
+    if (c->nranks > 1 && d->n_shared > 0 && d->shared_dofs) {
+        // how far the elements touching shared dofs reach in the element order (lpf_space_create puts them first): the
+        // overlapped halo exchange sends the interface as soon as these are done
+        std::vector<uint8_t> sh((size_t)c->ndof, 0);
+        for (int i = 0; i < d->n_shared; i++) sh[d->shared_dofs[i]] = 1;
+        for (int e = 0; e < c->ne; e++)
+            for (int k = 0; k < D3; k++) if (sh[d->gather[(size_t)e * D3 + k]]) { c->n_if_elems = e + 1; break; }
+    }
     {   // constrained map: essential dofs encoded as ~dof (gather reads 0, scatter skips)
         std::vector<uint8_t> em((size_t)c->ndof, 0);
         for (int i = 0; i < c->ness; i++) {
@@ -433,16 +441,24 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         // hp_x_ranges_needed[k] ranges of x, and range j of y is final after its last-touching chunk
         const bool ess_sorted = std::is_sorted(d->ess, d->ess + c->ness);
         if (c->ndof >= (1 << 18) && c->ne >= 64 && ess_sorted) {
-            const int K = 16, R = 32;
+            const int R = 32;
             const int rs = ((c->ndof + R - 1) / R + 511) & ~511;              // range size, 4 KB aligned
             for (int j = 0; j < R; j++) if ((long)j * rs < c->ndof) c->hp_range_end.push_back((int)std::min<long>((long)(j + 1) * rs, c->ndof));
             const int nr = (int)c->hp_range_end.size();
+            // element chunks: the interior elements [n_if, ne) in 16 chunks (their dofs ascend with the element index, so
+            // chunk k only needs a prefix of x), then the interface block [0, n_if) -- it reads both ends of the slab and its
+            // rows are final only after the halo-sum anyway
+            const int nif = (c->n_if_elems < c->ne) ? c->n_if_elems : 0, KI = 16;
+            for (int k = 0; k < KI; k++) {
+                c->hp_elem_begin.push_back(nif + (int)((long)(c->ne - nif) * k / KI));
+                c->hp_elem_end.push_back(nif + (int)((long)(c->ne - nif) * (k + 1) / KI));
+            }
+            if (nif > 0) { c->hp_elem_begin.push_back(0); c->hp_elem_end.push_back(nif); }
+            const int K = (int)c->hp_elem_end.size();
             std::vector<int> last_chunk(nr, 0);
             int run_max = 0;
             for (int k = 0; k < K; k++) {
-                const int ea = (int)((long)c->ne * k / K), eb = (int)((long)c->ne * (k + 1) / K);
-                c->hp_elem_end.push_back(eb);
-                for (int e = ea; e < eb; e++)
+                for (int e = c->hp_elem_begin[k]; e < c->hp_elem_end[k]; e++)
                     for (int q = 0; q < D3; q++) {
                         const int g = d->gather[(size_t)e * D3 + q];
                         run_max = std::max(run_max, g);
@@ -489,13 +505,6 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
         LPF_TRY(upload_halo(c->shalo, d->s_n_nbr, d->s_nbr_rank, d->s_nbr_offset, d->s_send, d->s_n_shared, d->s_shared,
                             d->s_red_off, d->s_red_src, &c->bytes));
         if (c->nranks <= LPF_P2P_MAXR) LPF_TRY(p2p_create(c));
-        // how far the elements touching shared dofs reach in the element order (lpf_space_create puts them first): the
-        // overlapped halo exchange sends the interface as soon as these are done
-        std::vector<uint8_t> sh((size_t)c->ndof, 0);
-        for (int i = 0; i < d->n_shared; i++) sh[d->shared_dofs[i]] = 1;
-        c->n_if_elems = 0;
-        for (int e = 0; e < c->ne; e++)
-            for (int k = 0; k < D3; k++) if (sh[d->gather[(size_t)e * D3 + k]]) { c->n_if_elems = e + 1; break; }
     }
     // surface tables
     if (c->nsurf > 0) {
@@ -800,7 +809,7 @@ static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
     int waited = 0, rc = LPF_OK;
     for (int k = 0; k < K && rc == LPF_OK; k++) {
         for (; waited < c->hp_x_ranges_needed[k]; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
-        c->sub_e0 = k ? c->hp_elem_end[k - 1] : 0;
+        c->sub_e0 = c->hp_elem_begin[k];
         c->sub_ne = c->hp_elem_end[k] - c->sub_e0;
         rc = apply_launch(c, c->gmap_c, x, y, nullptr, nullptr);
         c->sub_ne = -1;

@@ -37,7 +37,7 @@ __device__ __forceinline__ void apply_den_epilogue(double part, double *__restri
     if (tid == 0) {
         double s = 0.0;
         for (int i = 0; i < nw; i++) s += wsum[i];
-        atomicAdd(den_slots + (blockIdx.x & (LPF_DEN_SLOTS - 1)), s);
+        red_add_f64(den_slots + (blockIdx.x & (LPF_DEN_SLOTS - 1)), s);
     }
 }
 

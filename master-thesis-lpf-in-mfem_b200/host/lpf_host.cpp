@@ -705,15 +705,29 @@ Partition::Partition(const Mesh &mesh, const H1Space &space, int nranks_, int ra
         std::iota(l2g.begin(), l2g.end(), 0);
         g2l = l2g;
     }
-    for (int e = 0; e < neg; e++) {
-        if (elem_rank[e] != rank) continue;
-        elems.push_back(e);
-        for (int n = 0; n < D3; n++) {
-            const int g = space.gather[(size_t)e * D3 + n];
-            if (g2l[g] < 0) { g2l[g] = (int)l2g.size(); l2g.push_back(g); }
-            gather.push_back(g2l[g]);
+    // Local element order: the elements that touch a dof shared with another rank come FIRST (then the interior ones, each
+    // class in ascending global order).  The apply kernel walks the elements in order, so the interface is finished within
+    // its first wave of batches and the halo exchange overlaps the interior elements (csrc/p2p_dev.cuh, mode 2).
+    std::vector<uint64_t> touch(nranks > 1 ? space.ndof : 0, 0);
+    if (nranks > 1)
+        for (int e = 0; e < neg; e++)
+            for (int n = 0; n < D3; n++) touch[space.gather[(size_t)e * D3 + n]] |= 1ull << elem_rank[e];
+    auto on_interface = [&](int e) {
+        if (nranks == 1) return false;
+        for (int n = 0; n < D3; n++) if (touch[space.gather[(size_t)e * D3 + n]] & ~(1ull << rank)) return true;
+        return false;
+    };
+    for (int pass = 0; pass < 2; pass++) {
+        for (int e = 0; e < neg; e++) {
+            if (elem_rank[e] != rank || on_interface(e) != (pass == 0)) continue;
+            elems.push_back(e);
+            for (int n = 0; n < D3; n++) {
+                const int g = space.gather[(size_t)e * D3 + n];
+                if (g2l[g] < 0) { g2l[g] = (int)l2g.size(); l2g.push_back(g); }
+                gather.push_back(g2l[g]);
+            }
+            corners.insert(corners.end(), mesh.corners.begin() + (size_t)e * 24, mesh.corners.begin() + (size_t)(e + 1) * 24);
         }
-        corners.insert(corners.end(), mesh.corners.begin() + (size_t)e * 24, mesh.corners.begin() + (size_t)(e + 1) * 24);
     }
     if (nranks > 1) {
         // Local dofs in ascending GLOBAL id: the entity-based global numbering keeps the dofs of an edge / face / interior

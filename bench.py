@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-rk4", action="store_true", help="skip the PCG-per-RK-step measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rk4-refine", type=int, default=1)
+    ap.add_argument("--p2p-fuse", type=int, default=-1, help="N>1: option p2p_fuse (-1 = library default: halo exchange inside the apply kernel, overlapped)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: own NVLink peer-memory exchange or NCCL send/recv + all-reduce")
     return ap.parse_args()
 
@@ -192,6 +193,8 @@ def run_ours(a):
     stream = torch.cuda.current_stream().cuda_stream
     ctx = lpf.Context(sp, device=local, stream=stream)
     ctx.set_option("apply_variant", a.variant)
+    if a.p2p_fuse >= 0:
+        ctx.set_option("p2p_fuse", a.p2p_fuse)
     if world > 1 and a.comm == "p2p":
         ctx.p2p_connect(dist)
     elif world > 1:
@@ -327,7 +330,7 @@ def run_ours(a):
         "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": cfg,
-        "exchange": (("halo-sum inside the apply kernel over NVLink peer memory (own kernels), overlapped with interior elements" if a.comm == "p2p" else "NCCL send/recv + all-reduce") if world > 1 else None),
+        "exchange": ((("halo-sum inside the apply kernel over NVLink peer memory (own kernels), overlapped with interior elements" if a.p2p_fuse in (-1, 2) else f"NVLink peer memory (own kernels), p2p_fuse={a.p2p_fuse}") if a.comm == "p2p" else "NCCL send/recv + all-reduce") if world > 1 else None),
         "apply_variant": a.variant,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(p, sp.ne), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
@@ -363,6 +366,8 @@ def rk4_measure(lpf, torch, a, local, stream, world=1, rank=0, dist=None, weak=T
     mesh = lpf.Mesh.wave_tank(128 * nxf, 2, 16, Lx=1.0 * nxf).refine(refine)
     sp = lpf.Space(mesh, p, nranks=world, rank=rank)
     ctx = lpf.Context(sp, device=local, stream=stream)
+    if a.p2p_fuse >= 0:
+        ctx.set_option("p2p_fuse", a.p2p_fuse)
     if world > 1 and a.comm == "p2p":
         ctx.p2p_connect(dist)
     elif world > 1:

@@ -147,8 +147,16 @@ lpf_ctx *lpf_create(const lpf_space_desc *desc, int device, void *stream);
 void lpf_destroy(lpf_ctx *ctx);
 void *lpf_stream(lpf_ctx *ctx);
 int lpf_sync(lpf_ctx *ctx);                                   /* cudaStreamSynchronize */
-int lpf_ndof(const lpf_ctx *ctx);
-int lpf_nsurf(const lpf_ctx *ctx);
+int lpf_ndof(const lpf_ctx *ctx);                            /* local L-dofs            (pfes.GetVSize())     */
+int lpf_nsurf(const lpf_ctx *ctx);                           /* local surface L-dofs                          */
+/* T-vectors <-> L-vectors.  MFEM's solver-level vectors (FormLinearSystem, CGSolver, the ODE state) are T-vectors: the dofs
+ * a rank OWNS (pfes.GetTrueVSize()); this library computes on L-vectors (all local dofs, consistent copies of shared ones).
+ * which = 0: volume space, 1: free-surface space.  True dof t = the t-th owned L-dof in ascending order.  Serial: T == L.
+ *   lpf_prolong   P   (ConformingProlongationOperator::Mult / GroupCommunicator::Bcast)
+ *   lpf_restrict  R   (the owned entries; GetTrueDofs) */
+int lpf_ntrue(const lpf_ctx *ctx, int which);
+int lpf_prolong(lpf_ctx *ctx, int which, const double *xT_dev, double *xL_dev);
+int lpf_restrict(lpf_ctx *ctx, int which, const double *xL_dev, double *xT_dev);
 
 /* Multi-GPU plumbing: rank 0 calls lpf_comm_unique_id and ships the 128 bytes to the other ranks
  * (MPI_Bcast / torch.distributed); every rank then calls lpf_comm_init.  Replaces the MPI communicator

@@ -101,6 +101,9 @@ SIGNATURES = {
     "lpf_sync": (C.c_int, [_VP]),
     "lpf_ndof": (C.c_int, [_VP]),
     "lpf_nsurf": (C.c_int, [_VP]),
+    "lpf_ntrue": (C.c_int, [_VP, C.c_int]),
+    "lpf_prolong": (C.c_int, [_VP, C.c_int, _VP, _VP]),
+    "lpf_restrict": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "lpf_comm_unique_id": (C.c_int, [_VP]),
     "lpf_comm_init": (C.c_int, [_VP, _VP]),
     "lpf_p2p_export": (C.c_int, [_VP, _VP, C.POINTER(C.c_uint64), c_ip]),
@@ -421,6 +424,15 @@ class Context:
 
     def diag(self, out):
         _check(lib.lpf_diag(self.h, _ptr(out)), "lpf_diag")
+
+    def ntrue(self, which=0):
+        return lib.lpf_ntrue(self.h, which)
+
+    def prolong(self, xT, xL, which=0):
+        _check(lib.lpf_prolong(self.h, which, _ptr(xT), _ptr(xL)), "lpf_prolong")
+
+    def restrict(self, xL, xT, which=0):
+        _check(lib.lpf_restrict(self.h, which, _ptr(xL), _ptr(xT)), "lpf_restrict")
 
     def pa_diag_E(self, out):
         _check(lib.lpf_pa_diag_E(self.h, _ptr(out)), "lpf_pa_diag_E")

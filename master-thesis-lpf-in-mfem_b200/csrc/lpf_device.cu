@@ -74,6 +74,8 @@ struct lpf_ctx {
     bool affine_ok = false;   // decided by lpf_pa_setup
     int *gmap = nullptr, *gmap_c = nullptr, *ess = nullptr;
     uint8_t *essmask = nullptr, *owned = nullptr, *surf_owned = nullptr;
+    int ntrue[2] = {0, 0};            // owned (true) dofs of this rank: volume, surface
+    int *tdof[2] = {nullptr, nullptr}; // [ntrue] L-dof of true dof t (ascending); nullptr: T == L (serial)
     // solver vectors
     double *dinv = nullptr, *r = nullptr, *z = nullptr, *d = nullptr, *ad = nullptr, *X = nullptr, *Bv = nullptr, *tmp = nullptr;
     double *zdad = nullptr;   // backing store of z, d, ad
@@ -384,6 +386,7 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     c->p = d->order; c->D = d->order + 1; c->Q = d->order + 2;
     c->ne = d->ne; c->ndof = d->ndof; c->ness = d->n_ess; c->nsurf = d->n_surf;
     c->nranks = d->nranks > 0 ? d->nranks : 1; c->rank = d->rank;
+    c->ntrue[0] = d->ndof; c->ntrue[1] = d->n_surf;
     c->n_true_global = d->n_true_global ? d->n_true_global : d->ndof;
     const int D3 = c->D * c->D * c->D, Q3 = c->Q * c->Q * c->Q;
 
@@ -500,6 +503,16 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
     if (c->nranks > 1) {
         if (!d->owned) { lpf::set_error("lpf_create: multi-rank descriptor without ownership mask"); return LPF_ERR_ARG; }
         LPF_TRY(upload(c->owned, d->owned, n, &c->bytes));
+        {   // true-dof lists: T-vectors (MFEM's GetTrueVSize ordering: owned L-dofs in ascending order) <-> L-vectors
+            std::vector<int> t;
+            for (int i = 0; i < c->ndof; i++) if (d->owned[i]) t.push_back(i);
+            c->ntrue[0] = (int)t.size();
+            LPF_TRY(upload(c->tdof[0], t.data(), t.size(), &c->bytes));
+            t.clear();
+            if (d->surf_owned) for (int i = 0; i < c->nsurf; i++) if (d->surf_owned[i]) t.push_back(i);
+            c->ntrue[1] = (int)t.size();
+            LPF_TRY(upload(c->tdof[1], t.data(), t.size(), &c->bytes));
+        }
         LPF_TRY(upload_halo(c->halo, d->n_nbr, d->nbr_rank, d->nbr_offset, d->send_dofs, d->n_shared, d->shared_dofs,
                             d->red_off, d->red_src, &c->bytes));
         LPF_TRY(upload_halo(c->shalo, d->s_n_nbr, d->s_nbr_rank, d->s_nbr_offset, d->s_send, d->s_n_shared, d->s_shared,
@@ -609,7 +622,7 @@ void lpf_destroy(lpf_ctx *c)
     for (void *p : ptrs) if (p) cudaFree(p);
     free_halo(c->halo); free_halo(c->shalo);
     for (size_t r = 0; r < c->peers.size(); r++) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peers[r]);
-    void *pp[] = {c->box, c->p2p_local, c->p2p_done, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1]};
+    void *pp[] = {c->box, c->p2p_local, c->p2p_done, c->peers_dev, c->p2p_send_nbr[0], c->p2p_send_nbr[1], c->tdof[0], c->tdof[1]};
     for (void *p : pp) if (p) cudaFree(p);
     if (c->st_host) cudaFreeHost(c->st_host);
     if (c->state_pinned) cudaFreeHost(c->state_pinned);
@@ -637,6 +650,39 @@ int lpf_sync(lpf_ctx *c)
 }
 int lpf_ndof(const lpf_ctx *c) { return c ? c->ndof : LPF_ERR_ARG; }
 int lpf_nsurf(const lpf_ctx *c) { return c ? c->nsurf : LPF_ERR_ARG; }
+int lpf_ntrue(const lpf_ctx *c, int which) { return (c && (which == 0 || which == 1)) ? c->ntrue[which] : LPF_ERR_ARG; }
+
+// P: true dofs -> L-vector (the owner's value on every sharer).  Non-owned entries start at 0, the halo-sum then carries
+// the owner's value to them -- ConformingProlongationOperator::Mult + GroupCommunicator::Bcast of the reference's MFEM path.
+int lpf_prolong(lpf_ctx *c, int which, const double *xT, double *xL)
+{
+    if (!c || !xT || !xL || (which != 0 && which != 1)) { lpf::set_error("lpf_prolong: bad argument"); return LPF_ERR_ARG; }
+    const int nl = which == 0 ? c->ndof : c->nsurf, nt = c->ntrue[which];
+    if (nl == 0) return LPF_OK;
+    if (!c->tdof[which]) { CUDA_TRY(cudaMemcpyAsync(xL, xT, sizeof(double) * nl, cudaMemcpyDeviceToDevice, c->stream)); return LPF_OK; }
+    CUDA_TRY(cudaMemsetAsync(xL, 0, sizeof(double) * nl, c->stream));
+    if (nt) {
+        scatter_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(nt, c->tdof[which], xT, xL);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return halo_sum(c, which == 0 ? c->halo : c->shalo, xL);
+}
+
+// R: L-vector -> true dofs (the owned entries)
+int lpf_restrict(lpf_ctx *c, int which, const double *xL, double *xT)
+{
+    if (!c || !xT || !xL || (which != 0 && which != 1)) { lpf::set_error("lpf_restrict: bad argument"); return LPF_ERR_ARG; }
+    const int nl = which == 0 ? c->ndof : c->nsurf, nt = c->ntrue[which];
+    if (!c->tdof[which]) { if (nl) CUDA_TRY(cudaMemcpyAsync(xT, xL, sizeof(double) * nl, cudaMemcpyDeviceToDevice, c->stream)); return LPF_OK; }
+    if (nt) {
+        halo_pack_kernel<<<(nt + 255) / 256, 256, 0, c->stream>>>(nt, c->tdof[which], xL, xT);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    return LPF_OK;
+}
+
 long lpf_launch_count(lpf_ctx *c) { return c ? c->launches : 0; }
 size_t lpf_device_bytes(const lpf_ctx *c) { return c ? c->bytes : 0; }
 int lpf_affine_active(const lpf_ctx *c) { return c ? (int)(c->affine && c->affine_ok) : 0; }

@@ -13,3 +13,4 @@ timeout 300 $TR --master-port 29515 tools/check_multi_gpu.py --order 6 --mesh ta
 timeout 300 $TR --master-port 29516 tools/check_multi_gpu.py --order 4 --mesh tank --comm nccl > gpurun_out/r02_parity2_tank_nccl.txt 2>&1; echo "tank nccl rc=$?"; tail -3 gpurun_out/r02_parity2_tank_nccl.txt
 timeout 600 $TR --master-port 29517 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu > gpurun_out/r02_bench2_fuse2.log 2>&1; echo "bench2 rc=$?"; tail -1 gpurun_out/r02_bench2_fuse2.log
 timeout 300 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu > gpurun_out/r02_bench1.log 2>&1; echo "bench1 rc=$?"; tail -1 gpurun_out/r02_bench1.log
+timeout 600 $TR --master-port 29518 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu --p2p-fuse 0 > gpurun_out/r02_bench2_fuse0.log 2>&1; echo "bench2 fuse0 rc=$?"; tail -1 gpurun_out/r02_bench2_fuse0.log

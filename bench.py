@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-rk4", action="store_true", help="skip the PCG-per-RK-step measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rk4-refine", type=int, default=1)
+    ap.add_argument("--opt", action="append", default=[], help="extra lpf_set_option name=value (tuning A/B), repeatable")
     ap.add_argument("--p2p-fuse", type=int, default=-1, help="N>1: option p2p_fuse (-1 = library default: halo exchange inside the apply kernel, overlapped)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: own NVLink peer-memory exchange or NCCL send/recv + all-reduce")
     return ap.parse_args()
@@ -195,6 +196,8 @@ def run_ours(a):
     ctx.set_option("apply_variant", a.variant)
     if a.p2p_fuse >= 0:
         ctx.set_option("p2p_fuse", a.p2p_fuse)
+    for kv in a.opt:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if world > 1 and a.comm == "p2p":
         ctx.p2p_connect(dist)
     elif world > 1:
@@ -368,6 +371,8 @@ def rk4_measure(lpf, torch, a, local, stream, world=1, rank=0, dist=None, weak=T
     ctx = lpf.Context(sp, device=local, stream=stream)
     if a.p2p_fuse >= 0:
         ctx.set_option("p2p_fuse", a.p2p_fuse)
+    for kv in a.opt:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     if world > 1 and a.comm == "p2p":
         ctx.p2p_connect(dist)
     elif world > 1:

@@ -121,7 +121,9 @@ int lpf_space_rim(const lpf_space *s, int wall_attr, double cx, double cy, doubl
                   int *surf_idx, double *theta, int cap);
 /* f2  MacCamy-Fuchs linear diffraction by a vertical circular cylinder: |eta|_max / (H/2) at (r >= a, phi), phi
  * measured from the direction of propagation; the series of Solvers/cylinder-exact.cpp:53-115 (tol 1e-10, <= 400
- * terms there) with std::cyl_bessel_j / std::cyl_neumann in place of Boost.Math. */
+ * terms there) with std::cyl_bessel_j / std::cyl_neumann in place of Boost.Math.  tol > 0: the reference's stopping rule
+ * verbatim (:104-110).  tol < 0: tolerance |tol| with a robust rule (the reference's rule truncates the series to one
+ * term at phi = pi/2, where cos(m phi) makes the tested term vanish at m = 1). */
 double lpf_maccamy_fuchs(double k, double a, double r, double phi, double tol, int max_iter);
 /* f3  free-surface faces of this rank as order-p quads: conn[nf][(p+1)^2] local surface dofs, lexicographic in the
  * face's own axes (what ParaViewDataCollection writes for mesh_fs, :453-467).  conn = NULL: returns the count. */

@@ -193,6 +193,12 @@ public:
     B200Context(const B200Context &) = delete;
     B200Context &operator=(const B200Context &) = delete;
     lpf_ctx *get() const { return ctx_; }
+    /// The library enqueues on its own stream (CUDA graphs cannot be captured on MFEM's default stream).  MFEM's interfaces
+    /// are synchronous for the caller -- the next line of the driver may read the result on the host or launch an MFEM
+    /// kernel on the default stream -- so every adapter method ends with done().  [MFEM] With a real MFEM whose inputs were
+    /// produced by asynchronous device kernels, call MFEM_STREAM_SYNC before the adapter method (the stand-in's copies are
+    /// synchronous).
+    void done() const { check(lpf_sync(ctx_), "lpf_sync"); }
     /// T-vector -> device L-vector in a work buffer (which = 0 volume, 1 surface; two buffers per space)
     double *to_L(int which, int slot, const double *xT_dev) const
     {
@@ -217,14 +223,15 @@ private:
 class B200DiffusionIntegrator : public mfem::BilinearFormIntegrator {
 public:
     explicit B200DiffusionIntegrator(B200Context &c) : c_(c) {}
-    void AssemblePA(const mfem::FiniteElementSpace &) override { check(lpf_pa_setup(c_.get()), "lpf_pa_setup"); }
+    void AssemblePA(const mfem::FiniteElementSpace &) override { check(lpf_pa_setup(c_.get()), "lpf_pa_setup"); c_.done(); }
     void AddMultPA(const mfem::Vector &x, mfem::Vector &y) const override   // E-vectors, y += A_E x
     {
         check(lpf_pa_apply_E(c_.get(), x.Read(), y.ReadWrite()), "lpf_pa_apply_E");
+        c_.done();
     }
     /// E-vector diagonal, accumulated: what OperatorJacobiSmoother(*a_loc_cach, ess_tdof) (:124) reaches through
     /// BilinearForm::AssembleDiagonal -> AssembleDiagonalPA; MFEM then applies G^T and P^T itself.
-    void AssembleDiagonalPA(mfem::Vector &diag) override { check(lpf_pa_diag_E(c_.get(), diag.ReadWrite()), "lpf_pa_diag_E"); }
+    void AssembleDiagonalPA(mfem::Vector &diag) override { check(lpf_pa_diag_E(c_.get(), diag.ReadWrite()), "lpf_pa_diag_E"); c_.done(); }
 
 private:
     B200Context &c_;
@@ -242,12 +249,14 @@ public:
         double *xl = c_.to_L(0, 0, x.Read()), *yl = c_.work(0, 1);
         check(lpf_apply_T(c_.get(), xl, yl), "lpf_apply_T");
         check(lpf_restrict(c_.get(), 0, yl, y.Write()), "lpf_restrict");
+        c_.done();
     }
     void AssembleDiagonal(mfem::Vector &diag) const override
     {
         double *dl = c_.work(0, 0);
         check(lpf_diag(c_.get(), dl), "lpf_diag");
         check(lpf_restrict(c_.get(), 0, dl, diag.Write()), "lpf_restrict");
+        c_.done();
     }
 
 private:
@@ -268,6 +277,7 @@ public:
         double *bl = c_.to_L(0, 0, b.Read()), *xl = c_.to_L(0, 1, x.Read());
         check(lpf_pcg(c_.get(), bl, xl, rel_, abs_, max_iter_, &info_), "lpf_pcg");
         check(lpf_restrict(c_.get(), 0, xl, x.Write()), "lpf_restrict");
+        c_.done();
     }
     int GetNumIterations() const { return info_.iterations; }
     bool GetConverged() const { return info_.converged != 0; }
@@ -296,13 +306,14 @@ public:
     }
     /// eta envelope of cylinder-diffraction.cpp:410-444: call after every Step once t >= t_last_start
     void EnvelopeReset() { check(lpf_envelope_reset(c_.get()), "lpf_envelope_reset"); }
-    void EnvelopeUpdate(const mfem::Vector &state) { check(lpf_envelope_update(c_.get(), state_to_L(state, 0)), "lpf_envelope_update"); }
+    void EnvelopeUpdate(const mfem::Vector &state) { check(lpf_envelope_update(c_.get(), state_to_L(state, 0)), "lpf_envelope_update"); c_.done(); }
     void EnvelopeGet(mfem::Vector &env, double scale) { check(lpf_envelope_get(c_.get(), env.HostWrite(), scale), "lpf_envelope_get"); }
     void Mult(const mfem::Vector &x, mfem::Vector &dxdt) const override
     {
         double *xl = state_to_L(x, 0), *dl = c_.work(1, 1);
         check(lpf_rhs(c_.get(), GetTime(), xl, dl), "lpf_rhs");
         state_to_T(dl, dxdt);
+        c_.done();
     }
     /// [eta_T ; phi_T] -> [eta_L ; phi_L] in work buffer `slot` of the surface space, and back
     double *state_to_L(const mfem::Vector &xT, int slot) const
@@ -320,6 +331,7 @@ public:
         check(lpf_restrict(c_.get(), 1, xl + nl_, xt + nt_), "lpf_restrict");
     }
     lpf_ctx *ctx() const { return c_.get(); }
+    const B200Context &context() const { return c_; }
 
 private:
     B200Context &c_;
@@ -340,6 +352,7 @@ public:
         double *xl = rhs_->state_to_L(x, 0);
         check(lpf_rk4_step(rhs_->ctx(), xl, &t, dt), "lpf_rk4_step");
         rhs_->state_to_T(xl, x);
+        rhs_->context().done();
     }
 
 private:

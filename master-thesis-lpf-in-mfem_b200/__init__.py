@@ -533,9 +533,11 @@ def _hostptr(a):
     return a.data_ptr()
 
 
-def maccamy_fuchs(k, a, r, phi, tol=1e-10, max_iter=400):
-    """MacCamy-Fuchs envelope |eta|_max / (H/2) (cylinder-exact.cpp:53-115) through the C-ABI."""
+def maccamy_fuchs(k, a, r, phi, tol=1e-10, max_iter=400, robust=False):
+    """MacCamy-Fuchs envelope |eta|_max / (H/2) (cylinder-exact.cpp:53-115) through the C-ABI.  Default: the reference's
+    stopping rule verbatim; robust=True: the phi-independent rule (see lpf_b200.h)."""
     r, phi = np.broadcast_arrays(np.asarray(r, dtype=np.float64), np.asarray(phi, dtype=np.float64))
+    tol = -abs(tol) if robust else abs(tol)
     return np.array([lib.lpf_maccamy_fuchs(float(k), float(a), float(ri), float(pi), float(tol), int(max_iter))
                      for ri, pi in zip(r.ravel(), phi.ravel())]).reshape(r.shape)
 

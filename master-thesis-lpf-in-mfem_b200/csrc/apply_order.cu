@@ -26,7 +26,7 @@ int launch_persistent(LpfApplyArgs &a)
 {
     using C = TmaCfg<P, E, AFF>;
     constexpr int TS = TABS >= 0 ? TABS : (P >= 7 ? 1 : 0), TSO = TABS >= 0 ? TABS : (P >= 6 ? 1 : 0);
-    static int blocks_per_sm[16] = {0};
+    static int blocks_per_sm[2][16] = {{0}};
     void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs), (*kod)(const ApplyKArgs), (*kon)(const ApplyKArgs);
     if constexpr (EO) {
         kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, false, TS>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, false, TS>;
@@ -35,14 +35,17 @@ int launch_persistent(LpfApplyArgs &a)
         kd = pa_apply_tma_kernel<P, E, true, MINB, DET, false>; kn = pa_apply_tma_kernel<P, E, false, MINB, DET, false>;
         kod = pa_apply_tma_kernel<P, E, true, MINB, DET, true>; kon = pa_apply_tma_kernel<P, E, false, MINB, DET, true>;
     }
-    int &bps = blocks_per_sm[a.dev & 15];
+    const bool ovl = a.k.tail.mode != 0;             // multi-GPU: the halo-sum rides on this launch
+    // resident CTAs per SM of the kernel that is actually launched (the kernels with the exchange hooks need a few more
+    // registers: sizing the plain kernel's grid by them cost one CTA per SM at order 4 -- 14 % of a CG iteration)
+    int &bps = blocks_per_sm[ovl ? 1 : 0][a.dev & 15];
     if (bps == 0) {
         for (auto k : {kd, kn, kod, kon}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         int b0 = 0, b1 = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, kd, C::NT, C::SMEM_BYTES));
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, kod, C::NT, C::SMEM_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, ovl ? kod : kd, C::NT, C::SMEM_BYTES));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ovl ? kon : kn, C::NT, C::SMEM_BYTES));
         bps = std::max(1, std::min(b0, b1));
-        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, C::NT, (size_t)C::SMEM_BYTES, bps);
+        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d ovl=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, (int)ovl, C::NT, (size_t)C::SMEM_BYTES, bps);
     }
     const int nb = (a.k.ne + E - 1) / E;
     a.threads = C::NT; a.smem = C::SMEM_BYTES; a.grid = 0;
@@ -50,7 +53,6 @@ int launch_persistent(LpfApplyArgs &a)
     int grid = std::min(nb, a.max_ctas > 0 ? a.max_ctas : bps * a.sm_count);
     grid = std::min(grid, LPF_DEN_SLOTS);            // one (d, A d) slot per CTA
     a.grid = grid;
-    const bool ovl = a.k.tail.mode != 0;             // multi-GPU: the halo-sum rides on this launch
     if (a.k.tail.mode == 2) a.k.tail.n_if_batches = (a.k.tail.n_if_batches + E - 1) / E;     // elements -> batches
     CUDA_TRY(launch_ex(a.pdl, a.k.den_slots ? (ovl ? kod : kd) : (ovl ? kon : kn), dim3(grid), dim3(C::NT), C::SMEM_BYTES, a.stream, a.k));
     CUDA_TRY(cudaGetLastError());
@@ -74,7 +76,7 @@ int launch_default(LpfApplyArgs &a)
         if constexpr (P == 1) return launch_persistent<16, 3, false, false, DET>(a);
         else if constexpr (P == 2) return launch_persistent<8, 3, false, false, DET>(a);
         else if constexpr (P == 3) return launch_persistent<8, 2, true, false, DET>(a);
-        else if constexpr (P == 4) return launch_persistent<3, 3, true, false, DET>(a);
+        else if constexpr (P == 4) return launch_persistent<3, 4, true, false, DET>(a);
         else if constexpr (P == 5) return launch_persistent<3, 2, true, false, DET>(a);
         else if constexpr (P == 6) return launch_persistent<2, 3, true, false, DET>(a);
         else if constexpr (P == 7) return launch_persistent<1, 3, true, false, DET>(a);
@@ -105,7 +107,7 @@ int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
         if constexpr (P == 1) { if (v == 31) return launch_persistent<32, 2, true>(a); return launch_persistent<16, 3, true>(a); }
         else if constexpr (P == 2) { if (v == 31) return launch_persistent<16, 2, true>(a); return launch_persistent<8, 3, true>(a); }
         else if constexpr (P == 3) { if (v == 31) return launch_persistent<5, 4, true>(a); return launch_persistent<5, 3, true>(a); }
-        else if constexpr (P == 4) { if (v == 31) return launch_persistent<4, 3, true>(a); if (v == 32) return launch_persistent<2, 5, true>(a); return launch_persistent<3, 4, true>(a); }
+        else if constexpr (P == 4) { if (v == 31) return launch_persistent<4, 3, true>(a); if (v == 32) return launch_persistent<2, 5, true>(a); return launch_persistent<3, 3, true>(a); }
         else if constexpr (P == 5) { if (v == 31) return launch_persistent<2, 4, true>(a); if (v == 32) return launch_persistent<3, 2, true, false, false, 1>(a); return launch_persistent<2, 3, true>(a); }
         else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); if (v == 32) return launch_persistent<2, 2, true, false, false, 1>(a); return launch_persistent<2, 2, true>(a); }
         else if constexpr (P == 7) {

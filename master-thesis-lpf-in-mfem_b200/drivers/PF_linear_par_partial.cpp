@@ -42,6 +42,7 @@ int main(int argc, char *argv[])
         printf("%g\nRunning on %d GPUs\nStarting time integration with %d steps\n", dt, num_procs, nsteps);
 
         World world(num_procs, std::string(a.get("--comm", "p2p")) == "nccl");
+        world.parse_options(a.get("--opt", ""));   // e.g. --opt affine=0,deterministic=1 (lpf_set_option)
         std::mutex io;
         double eta_max_global = 0.0;
         world.run([&](int myid) {

@@ -36,6 +36,7 @@ int main(int argc, char *argv[])
         mesh->GetBoundingBox(lo, hi);
 
         World world(num_procs, std::string(a.get("--comm", "p2p")) == "nccl");
+        world.parse_options(a.get("--opt", ""));   // e.g. --opt affine=0,deterministic=1 (lpf_set_option)
         std::mutex io;
         std::vector<std::pair<double, double>> cyl_eta;           // gathered over the ranks (MPI_Allgatherv in the reference)
         long its_total = 0;
@@ -113,7 +114,7 @@ int main(int argc, char *argv[])
         int n = 0;
         for (auto &p : cyl_eta) {
             if (p.first - prev_th < 1e-10) continue;                                        // :589
-            const double ex = lpf_maccamy_fuchs(w.k, rad, rad, p.first, 1e-10, 400);
+            const double ex = lpf_maccamy_fuchs(w.k, rad, rad, p.first, a.has("--exact-robust") ? -1e-10 : 1e-10, 400);
             fout << p.first << " " << p.second << " " << ex << "\n";
             printf("rim theta = %.6f  2 eta_max / H = %.6f   MacCamy-Fuchs %.6f\n", p.first, p.second, ex);
             err2 += (p.second - ex) * (p.second - ex);

@@ -167,6 +167,18 @@ struct World {
     std::vector<uint64_t> raw_ptrs;    // mailboxes of all ranks (threads of one process share the address space)
     std::vector<int> devices;
     ThreadBarrier barrier;
+    std::vector<std::pair<std::string, long>> options;   // lpf_set_option pairs for every context (--opt name=value,name=value)
+    void parse_options(const char *spec)
+    {
+        std::string s(spec ? spec : "");
+        size_t a = 0;
+        while (a < s.size()) {
+            const size_t b = s.find(',', a), e = s.find('=', a);
+            if (e != std::string::npos) options.emplace_back(s.substr(a, e - a), std::atol(s.substr(e + 1, b == std::string::npos ? b : b - e - 1).c_str()));
+            if (b == std::string::npos) break;
+            a = b + 1;
+        }
+    }
     explicit World(int n, bool nccl = false) : nranks(n), use_nccl(nccl), raw_ptrs(n, 0), devices(n, 0), barrier(n)
     {
         if (n > 1 && use_nccl) check(lpf_comm_unique_id(nccl_id), "lpf_comm_unique_id");
@@ -191,6 +203,7 @@ public:
     {
         ctx_ = lpf_create(&sp.desc, device, nullptr);
         if (!ctx_) throw std::runtime_error(std::string("lpf_create: ") + lpf_last_error());
+        for (auto &o : world.options) check(lpf_set_option(ctx_, o.first.c_str(), o.second), "lpf_set_option");
         if (sp.desc.nranks > 1 && world.use_nccl) check(lpf_comm_init(ctx_, world.nccl_id), "lpf_comm_init");
         else if (sp.desc.nranks > 1) {
             // replaces MPI_COMM_WORLD inside CGSolver / GroupCommunicator: peer-memory mailboxes over NVLink
@@ -215,6 +228,19 @@ public:
     void SetState(const std::vector<double> &s) { if (ns_) check(lpf_memcpy_h2d(state_, s.data(), sizeof(double) * 2 * ns_), "h2d"); }
     void GetState(std::vector<double> &s) { s.resize(2 * (size_t)ns_); check(lpf_sync(ctx_), "sync"); if (ns_) check(lpf_memcpy_d2h(s.data(), state_, sizeof(double) * 2 * ns_), "d2h"); }
     void Step(double &t, double dt) { check(lpf_rk4_step(ctx_, state_, &t, dt), "ode_solver->Step"); }   // :494
+    /// w~ = d(phi)/dz on the free surface for the CURRENT state at time t (rhs_linear::GetWTilde() of
+    /// convergence-parallel-partial-hconv.cpp:331: the first half of rhs_linear::Mult's output without relaxation zones)
+    std::vector<double> WTilde(double t)
+    {
+        std::vector<double> w((size_t)ns_);
+        double *d = (double *)lpf_dev_alloc(sizeof(double) * 2 * (ns_ ? ns_ : 1));
+        if (!d) throw std::runtime_error(lpf_last_error());
+        check(lpf_rhs(ctx_, t, state_, d), "rhs_linear::Mult");
+        check(lpf_sync(ctx_), "sync");
+        if (ns_) check(lpf_memcpy_d2h(w.data(), d, sizeof(double) * ns_), "d2h");
+        lpf_dev_free(d);
+        return w;
+    }
     void Sync() { check(lpf_sync(ctx_), "sync"); }
     std::vector<int> LastIterations()
     {

@@ -45,6 +45,7 @@ int main(int argc, char *argv[])
             std::unique_ptr<Mesh> mesh(Mesh::FromName(mesh_name));
             for (int i = 0; i < par_ref_levels; i++) mesh->UniformRefinement();
             World world(num_procs, std::string(a.get("--comm", "p2p")) == "nccl");
+            world.parse_options(a.get("--opt", ""));   // e.g. --opt affine=0,deterministic=1 (lpf_set_option)
             std::mutex mu;
             double max_time = 0.0;
             long dofs = 0;

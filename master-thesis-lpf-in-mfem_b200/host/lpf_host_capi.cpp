@@ -164,16 +164,23 @@ int lpf_space_desc_get(const lpf_space *s, lpf_space_desc *d)
     return LPF_OK;
 }
 
-// |eta|_max / (H/2) on r >= a at angle phi from the direction of propagation (cylinder-exact.cpp:53-115)
+// |eta|_max / (H/2) on r >= a at angle phi from the direction of propagation (cylinder-exact.cpp:53-115).
+// tol > 0: the reference's stopping rule verbatim (:104-110): stop when |Re(term)| of two consecutive terms is below tol,
+//          the "previous term" starting at 0.
+// tol < 0: robust rule with tolerance |tol|: the phi-independent coefficient of two consecutive terms is tested instead.
+//          (The reference's rule carries cos(m phi) inside the tested term, so at phi = pi/2 it fires at m = 1 -- cos = 0,
+//          previous term 0 -- and truncates the series to its m = 0 term; everywhere else the two rules agree to ~tol.)
 double lpf_maccamy_fuchs(double k, double a, double r, double phi, double tol, int max_iter)
 {
     using cd = std::complex<double>;
+    const bool robust = tol < 0.0;
+    const double etol = std::fabs(tol);
     const double ka = k * a, kr = k * r;
     const double J0P = -std::cyl_bessel_j(1.0, ka);
     const cd H0P(-std::cyl_bessel_j(1.0, ka), -std::cyl_neumann(1.0, ka));
     const cd H0r(std::cyl_bessel_j(0.0, kr), std::cyl_neumann(0.0, kr));
     cd E = std::cyl_bessel_j(0.0, kr) - H0r * (J0P / H0P);
-    double oldterm = 1.0;
+    double oldterm = robust ? 1.0 : 0.0;
     for (int m = 1; m <= max_iter; m++) {
         const double JmP = 0.5 * (std::cyl_bessel_j(m - 1.0, ka) - std::cyl_bessel_j(m + 1.0, ka));
         const cd HmP(JmP, 0.5 * (std::cyl_neumann(m - 1.0, ka) - std::cyl_neumann(m + 1.0, ka)));
@@ -185,12 +192,8 @@ double lpf_maccamy_fuchs(double k, double a, double r, double phi, double tol, i
         const cd term = coef * std::cos(m * phi);
         if (std::isnan(term.real())) break;
         E += term;
-        // The reference stops when Re(term) of two consecutive terms is below tol (cylinder-exact.cpp:104-110); with the
-        // cos(m phi) factor inside, that fires at m = 1 for phi = pi/2 (cos = 0, oldterm = 0) and truncates the series to
-        // its m = 0 term.  We test the phi-independent coefficient instead: same values to ~tol wherever the reference's
-        // rule does not fire spuriously, and correct at phi = pi/2.
-        const double nextterm = std::abs(coef);
-        if (nextterm < tol && oldterm < tol) break;
+        const double nextterm = robust ? std::abs(coef) : term.real();
+        if (std::fabs(nextterm) < etol && std::fabs(oldterm) < etol) break;
         oldterm = nextterm;
     }
     return std::abs(E);

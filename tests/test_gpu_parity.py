@@ -180,7 +180,7 @@ def test_api_state_errors(lpf, cuda, tank):
     ctx.close()
 
 
-@pytest.mark.parametrize("p,rel", [(2, 1e-12), (4, 1e-12), (4, 1e-8), (6, 1e-12)])
+@pytest.mark.parametrize("p,rel", [(2, 1e-12), (4, 1e-12), (4, 1e-8), (6, 1e-12), (9, 1e-12), (10, 1e-12)])
 def test_laplace_solve_matches_oracle_pcg(lpf, orc, cuda, tank, p, rel):
     """FormLinearSystem + CGSolver(Jacobi) + RecoverFEMSolution: iterations +-1, potential 1e-10."""
     torch = cuda

@@ -262,7 +262,7 @@ long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launche
  *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30-34 = alternative (E, CTAs/SM) pairs
  *   "affine" [1]          affine fast path when every element is affine (lpf_affine_active)
  *   "use_graph" [1], "pcg_chunk" [16]   CUDA graph of pcg_chunk CG iterations, status polled once per chunk
- *   "pdl" [1]             programmatic dependent launch between the kernels of a CG iteration
+ *   "pdl" [0]             programmatic dependent launch between the kernels of a CG iteration (round 2: slower, off)
  *   "skip_zero_apply" [1] skip the initial-residual apply when the guess is zero off the essential dofs (exact)
  *   "p2p_fuse" [2]        multi-GPU halo-sum of an apply: 0 = separate LL kernel, 1 = last CTA of the apply kernel (only while
  *                         the interface has <= "p2p_fuse_max" [2048] entries), 2 = inside the apply kernel, overlapped with the

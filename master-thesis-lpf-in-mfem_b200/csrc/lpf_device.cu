@@ -56,7 +56,8 @@ struct lpf_ctx {
     // options
     int variant = 0;          // apply kernel variant (elements per CTA / prefetch), see apply_launch
     int use_graph = 1, chunk = 16, skip_zero_apply = 1;
-    int pdl = 1;              // programmatic dependent launch between the kernels of a PCG iteration
+    int pdl = 0;              // programmatic dependent launch between the kernels of a PCG iteration (measured slower in
+                              // round 2 on every size and GPU count, profiles/r02_pcg_ab.txt: off by default)
     bool pdl_now = false;     // set while pcg_iteration() enqueues
     int max_ctas = 0;
     int verbose = 0;

@@ -146,13 +146,6 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
             for (int i = 0; i < 6; i++) da[i] = __ldg(de + i);
         }
 
-        if (tid == 0 && has_next) {
-            const int n1 = batch_elems(bn);
-            fence_proxy_async();
-            mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
-            bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
-        }
-
         // ---- X stage: (B_x u, G_x u) on the line (dz,dy) ----
         if (xvalid) {
             double e[DC], o[DH], sb[Q], sg[Q];
@@ -164,6 +157,13 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
             for (int q = 0; q < Q; q++) { a[q] = sb[q]; a[C::SAA + q] = sg[q]; }
         }
         __syncthreads();
+        // gather map of the next batch (issued behind the first barrier after the previous batch's Xt stage, pa_apply_tma.cuh)
+        if (tid == 0 && has_next) {
+            const int n1 = batch_elems(bn);
+            fence_proxy_async();
+            mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
+            bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
+        }
 
         // ---- Y stage: line (dz,qx) ----
         if (yvalid) {

@@ -41,8 +41,11 @@ __device__ __forceinline__ void apply_den_epilogue(double part, double *__restri
     }
 }
 
-// end of one batch: the __syncthreads that frees the stage buffers for the next batch, plus (multi-GPU, overlapped halo
-// exchange) the bookkeeping of the interface batches
+// End of one batch.  The single-GPU kernels need NO barrier here: the X stage of the next batch writes exactly the
+// shared-memory line its own thread has just read in the Xt stage (same thread <-> line map), the B buffer is not touched
+// before the next Y stage, and the gather-map copy that reuses this batch's index buffer is issued behind the next
+// barrier (one CTA-wide barrier less per batch: the barrier was the largest stall of the order-4 kernel).  The kernels that
+// carry the overlapped halo exchange keep it for the bookkeeping of the interface batches.
 template <bool OVL>
 __device__ __forceinline__ void apply_batch_end(const P2PTail &tail, P2POverlap &ov, int b, const double *__restrict__ y)
 {
@@ -52,7 +55,7 @@ __device__ __forceinline__ void apply_batch_end(const P2PTail &tail, P2POverlap 
         __syncthreads();
         if (ifb && threadIdx.x == 0) atomicAdd(&tail.d.local->if_done, 1u);
         p2p_if_try_send(tail, ov, y);
-    } else {
+    } else if (OVL) {
         __syncthreads();
     }
 }
@@ -142,14 +145,6 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
         const LpfOrderTab<P> &T = c_ot[it >> 30];
 #define BGL(q, i) (reinterpret_cast<const double2 *>(T.BG)[(q) * D + (i)])     /* {B, G}[q][i]: one LDCU.128 */
 
-        // gather map of the next batch -> the other index buffer (last read two stages ago, before a barrier)
-        if (tid == 0 && has_next) {
-            const int n1 = batch_elems(bn);
-            fence_proxy_async();
-            mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
-            bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
-        }
-
         // ---- X stage ----
         if (xvalid) {
             double *a = smem + ex * C::ES + xdz * C::SAZ + xdy * C::SAY;
@@ -163,6 +158,15 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
             }
         }
         __syncthreads();
+        // gather map of the next batch -> the other index buffer.  Its last readers were the Xt threads of the PREVIOUS batch
+        // (their scatter indices); there is no barrier at the end of a batch any more (see apply_batch_end), so the copy is
+        // issued here, behind the first barrier every thread passes after that Xt stage.
+        if (tid == 0 && has_next) {
+            const int n1 = batch_elems(bn);
+            fence_proxy_async();
+            mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
+            bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
+        }
 
         // ---- Y stage ----
         if (yvalid) {
@@ -290,7 +294,7 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
 #pragma unroll
             for (int i = 0; i < D; i++) xs[i] = xsn[i];
         }
-        apply_batch_end<OVL>(ka.tail, ov, b, y);     // smem A is rewritten by X(b') and index buffer `cur` by the copy issued next
+        apply_batch_end<OVL>(ka.tail, ov, b, y);
 #undef BGL
     }
 

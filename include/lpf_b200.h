@@ -259,7 +259,8 @@ long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launche
  *   "deterministic" [0]   1 = bit-reproducible results: the restriction-transpose is an ordered gather (element order, as
  *                         MFEM's CPU ElementRestriction::MultTranspose) of an E-vector instead of red.global.add, the
  *                         diagonal likewise; CG iteration counts are then identical from run to run.  ~20 % slower apply.
- *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30-34 = alternative (E, CTAs/SM) pairs
+ *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30 = an alternative (E, CTAs/SM) pair;
+ *                         33 = the round-1 kernels of orders 7 / 8 (kept as evidence for profiles/r02_sweep_orders.txt)
  *   "affine" [1]          affine fast path when every element is affine (lpf_affine_active)
  *   "use_graph" [1], "pcg_chunk" [16]   CUDA graph of pcg_chunk CG iterations, status polled once per chunk
  *   "pdl" [0]             programmatic dependent launch between the kernels of a CG iteration (round 2: slower, off)

@@ -62,10 +62,13 @@ struct TmaCfg : ApplyCfg<P, E> {
 template <int P>
 struct __align__(16) LpfOrderTab {
     static constexpr int D = P + 1, Q = P + 2, MH = (Q + 1) / 2;
+    // rows of the half tables are padded to an even number of doubles and every array has an even length, so that two
+    // neighbouring coefficients of a row can be fetched by ONE 16-byte uniform load (LDCU.128)
+    static constexpr int RS = (MH + 1) & ~1;
     double BG[2 * Q * D];
     double qwts[Q + (Q & 1)];
-    double BeF[MH * MH], BoF[MH * MH], GeF[MH * MH], GoF[MH * MH];   // [QC][DC], [QC][DH]
-    double BeT[MH * MH], BoT[MH * MH], GeT[MH * MH], GoT[MH * MH];   // [DC][QC], [DC][QH]
+    double BeF[MH * RS], BoF[MH * RS], GeF[MH * RS], GoF[MH * RS];   // [QC][RS] (DC used), [QC][RS] (DH used)
+    double BeT[MH * RS], BoT[MH * RS], GeT[MH * RS], GoT[MH * RS];   // [DC][RS] (QC used), [DC][RS] (QH used)
 };
 
 #ifdef LPF_ORDER

@@ -21,26 +21,29 @@ constexpr int P = LPF_ORDER;
 // TABS < 0: the order's default (one coefficient-table copy per stage from order 7 up, from order 6 up in the kernels that
 // carry the overlapped halo exchange -- the variants where ptxas otherwise falls back to per-thread LDC loads,
 // profiles/r02_sass_opcodes.md)
-template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1>
+template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1, bool WOVL = false>
 int launch_persistent(LpfApplyArgs &a)
 {
     using C = TmaCfg<P, E, AFF>;
     constexpr int TS = TABS >= 0 ? TABS : (P >= 7 ? 1 : 0), TSO = TABS >= 0 ? TABS : (P >= 6 ? 1 : 0);
     static int blocks_per_sm[2][16] = {{0}};
-    void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs), (*kod)(const ApplyKArgs), (*kon)(const ApplyKArgs);
+    // WOVL: also instantiate the kernels that carry the multi-GPU exchange hooks (tuned default and affine kernels only; the
+    // alternative variants of the tuning sweep exchange through the separate LL kernel, lpf_device.cu tail_mode)
+    void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs), (*kod)(const ApplyKArgs) = nullptr, (*kon)(const ApplyKArgs) = nullptr;
     if constexpr (EO) {
         kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, false, TS>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, false, TS>;
-        kod = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, true, TSO>; kon = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, true, TSO>;
+        if constexpr (WOVL) { kod = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, true, TSO>; kon = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, true, TSO>; }
     } else {
         kd = pa_apply_tma_kernel<P, E, true, MINB, DET, false>; kn = pa_apply_tma_kernel<P, E, false, MINB, DET, false>;
-        kod = pa_apply_tma_kernel<P, E, true, MINB, DET, true>; kon = pa_apply_tma_kernel<P, E, false, MINB, DET, true>;
+        if constexpr (WOVL) { kod = pa_apply_tma_kernel<P, E, true, MINB, DET, true>; kon = pa_apply_tma_kernel<P, E, false, MINB, DET, true>; }
     }
+    if (!WOVL && a.k.tail.mode != 0) { lpf::set_error("this apply_variant has no exchange hooks"); return LPF_ERR_UNSUPPORTED; }
     const bool ovl = a.k.tail.mode != 0;             // multi-GPU: the halo-sum rides on this launch
     // resident CTAs per SM of the kernel that is actually launched (the kernels with the exchange hooks need a few more
     // registers: sizing the plain kernel's grid by them cost one CTA per SM at order 4 -- 14 % of a CG iteration)
     int &bps = blocks_per_sm[ovl ? 1 : 0][a.dev & 15];
     if (bps == 0) {
-        for (auto k : {kd, kn, kod, kon}) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
+        for (auto k : {kd, kn, kod, kon}) if (k) CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
         int b0 = 0, b1 = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, ovl ? kod : kd, C::NT, C::SMEM_BYTES));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ovl ? kon : kn, C::NT, C::SMEM_BYTES));
@@ -65,23 +68,23 @@ template <bool AFF, bool DET>
 int launch_default(LpfApplyArgs &a)
 {
     if constexpr (AFF) {
-        if constexpr (P == 1) return launch_persistent<16, 4, true, true>(a);
-        else if constexpr (P == 2) return launch_persistent<8, 4, true, true>(a);
-        else if constexpr (P == 3) return launch_persistent<8, 2, true, true>(a);
-        else if constexpr (P == 4) return launch_persistent<3, 4, true, true>(a);
-        else if constexpr (P == 5) return launch_persistent<3, 2, true, true>(a);
-        else if constexpr (P == 6) return launch_persistent<2, 3, true, true>(a);
-        else return launch_persistent<1, 2, true, true>(a);
+        if constexpr (P == 1) return launch_persistent<16, 4, true, true, false, -1, true>(a);
+        else if constexpr (P == 2) return launch_persistent<8, 4, true, true, false, -1, true>(a);
+        else if constexpr (P == 3) return launch_persistent<8, 2, true, true, false, -1, true>(a);
+        else if constexpr (P == 4) return launch_persistent<3, 4, true, true, false, -1, true>(a);
+        else if constexpr (P == 5) return launch_persistent<3, 2, true, true, false, -1, true>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 3, true, true, false, -1, true>(a);
+        else return launch_persistent<1, 2, true, true, false, -1, true>(a);
     } else {
-        if constexpr (P == 1) return launch_persistent<16, 3, false, false, DET>(a);
-        else if constexpr (P == 2) return launch_persistent<8, 3, false, false, DET>(a);
-        else if constexpr (P == 3) return launch_persistent<8, 2, true, false, DET>(a);
-        else if constexpr (P == 4) return launch_persistent<3, 4, true, false, DET>(a);
-        else if constexpr (P == 5) return launch_persistent<3, 2, true, false, DET>(a);
-        else if constexpr (P == 6) return launch_persistent<2, 3, true, false, DET>(a);
-        else if constexpr (P == 7) return launch_persistent<1, 3, true, false, DET>(a);
-        else if constexpr (P == 8) return launch_persistent<1, 2, true, false, DET>(a);
-        else return launch_persistent<1, 1, true, false, DET>(a);
+        if constexpr (P == 1) return launch_persistent<16, 3, false, false, DET, -1, !DET>(a);
+        else if constexpr (P == 2) return launch_persistent<8, 3, false, false, DET, -1, !DET>(a);
+        else if constexpr (P == 3) return launch_persistent<8, 2, true, false, DET, -1, !DET>(a);
+        else if constexpr (P == 4) return launch_persistent<3, 4, true, false, DET, -1, !DET>(a);
+        else if constexpr (P == 5) return launch_persistent<3, 2, true, false, DET, -1, !DET>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 3, true, false, DET, -1, !DET>(a);
+        else if constexpr (P == 7) return launch_persistent<1, 3, true, false, DET, -1, !DET>(a);
+        else if constexpr (P == 8) return launch_persistent<1, 2, true, false, DET, -1, !DET>(a);
+        else return launch_persistent<1, 1, true, false, DET, -1, !DET>(a);
     }
 }
 
@@ -103,25 +106,16 @@ int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
         else if constexpr (P <= 8) return launch_persistent<2, 1, false>(a);
         else return launch_persistent<1, 1, false>(a);
     }
-    if (v >= 30 && v < 40) {      // even-odd contractions: alternative (E, CTAs/SM, table copies) for the tuning sweep
-        if constexpr (P == 1) { if (v == 31) return launch_persistent<32, 2, true>(a); return launch_persistent<16, 3, true>(a); }
-        else if constexpr (P == 2) { if (v == 31) return launch_persistent<16, 2, true>(a); return launch_persistent<8, 3, true>(a); }
-        else if constexpr (P == 3) { if (v == 31) return launch_persistent<5, 4, true>(a); return launch_persistent<5, 3, true>(a); }
-        else if constexpr (P == 4) { if (v == 31) return launch_persistent<4, 3, true>(a); if (v == 32) return launch_persistent<2, 5, true>(a); return launch_persistent<3, 3, true>(a); }
-        else if constexpr (P == 5) { if (v == 31) return launch_persistent<2, 4, true>(a); if (v == 32) return launch_persistent<3, 2, true, false, false, 1>(a); return launch_persistent<2, 3, true>(a); }
-        else if constexpr (P == 6) { if (v == 31) return launch_persistent<3, 1, true>(a); if (v == 32) return launch_persistent<2, 2, true, false, false, 1>(a); return launch_persistent<2, 2, true>(a); }
-        else if constexpr (P == 7) {
-            if (v == 31) return launch_persistent<2, 2, true>(a);
-            if (v == 32) return launch_persistent<1, 2, true>(a);
-            if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a);      // the round-1 kernel (per-thread LDC)
-            if (v == 34) return launch_persistent<1, 3, true, false, false, 0>(a);
-            return launch_persistent<2, 1, true>(a);
-        }
-        else if constexpr (P == 8) {
-            if (v == 31) return launch_persistent<2, 1, true>(a);
-            if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a);      // the round-1 kernel (per-thread LDC)
-            return launch_persistent<1, 2, true>(a);
-        }
+    if (v >= 30 && v < 40) {      // even-odd contractions: one alternative (E, CTAs/SM) per order (tests, tuning sweep);
+                                  // 33: the round-1 kernels of orders 7 / 8 (per-thread LDC coefficient loads) as evidence
+        if constexpr (P == 1) return launch_persistent<16, 3, true>(a);
+        else if constexpr (P == 2) return launch_persistent<8, 3, true>(a);
+        else if constexpr (P == 3) return launch_persistent<5, 3, true>(a);
+        else if constexpr (P == 4) return launch_persistent<2, 5, true>(a);
+        else if constexpr (P == 5) return launch_persistent<2, 3, true>(a);
+        else if constexpr (P == 6) return launch_persistent<2, 2, true, false, false, 1>(a);
+        else if constexpr (P == 7) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<1, 2, true>(a); }
+        else if constexpr (P == 8) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<2, 1, true>(a); }
         else return launch_default<false, false>(a);
     }
     lpf::set_error("unknown apply_variant " + std::to_string(v));
@@ -152,7 +146,7 @@ int LPF_CAT(lpf_apply_E_p, LPF_ORDER)(const double *qd, const double *xE, double
 // them to the CURRENT device
 int LPF_CAT(lpf_apply_tables_p, LPF_ORDER)(const double *B, const double *G, const double *qwts)
 {
-    constexpr int D = P + 1, Q = P + 2, DC = (D + 1) / 2, DH = D / 2, QC = (Q + 1) / 2, QH = Q / 2;
+    constexpr int D = P + 1, Q = P + 2, DC = (D + 1) / 2, DH = D / 2, QC = (Q + 1) / 2, QH = Q / 2, RS = LpfOrderTab<P>::RS;
     std::vector<LpfOrderTab<P>> tabs(LPF_TAB_COPIES);
     LpfOrderTab<P> &t = tabs[0];
     std::memset(&t, 0, sizeof(t));
@@ -162,22 +156,22 @@ int LPF_CAT(lpf_apply_tables_p, LPF_ORDER)(const double *B, const double *G, con
     for (int q = 0; q < Q; q++) t.qwts[q] = qwts[q];
     for (int q = 0; q < QC; q++) {
         for (int d = 0; d < DC; d++) {
-            t.BeF[q * DC + d] = d < DH ? 0.5 * (Bm(q, d) + Bm(q, D - 1 - d)) : Bm(q, d);
-            t.GeF[q * DC + d] = d < DH ? 0.5 * (Gm(q, d) + Gm(q, D - 1 - d)) : Gm(q, d);
+            t.BeF[q * RS + d] = d < DH ? 0.5 * (Bm(q, d) + Bm(q, D - 1 - d)) : Bm(q, d);
+            t.GeF[q * RS + d] = d < DH ? 0.5 * (Gm(q, d) + Gm(q, D - 1 - d)) : Gm(q, d);
         }
         for (int d = 0; d < DH; d++) {
-            t.BoF[q * DH + d] = 0.5 * (Bm(q, d) - Bm(q, D - 1 - d));
-            t.GoF[q * DH + d] = 0.5 * (Gm(q, d) - Gm(q, D - 1 - d));
+            t.BoF[q * RS + d] = 0.5 * (Bm(q, d) - Bm(q, D - 1 - d));
+            t.GoF[q * RS + d] = 0.5 * (Gm(q, d) - Gm(q, D - 1 - d));
         }
     }
     for (int d = 0; d < DC; d++) {
         for (int q = 0; q < QC; q++) {
-            t.BeT[d * QC + q] = q < QH ? 0.5 * (Bm(q, d) + Bm(Q - 1 - q, d)) : Bm(q, d);
-            t.GeT[d * QC + q] = q < QH ? 0.5 * (Gm(q, d) + Gm(Q - 1 - q, d)) : Gm(q, d);
+            t.BeT[d * RS + q] = q < QH ? 0.5 * (Bm(q, d) + Bm(Q - 1 - q, d)) : Bm(q, d);
+            t.GeT[d * RS + q] = q < QH ? 0.5 * (Gm(q, d) + Gm(Q - 1 - q, d)) : Gm(q, d);
         }
         for (int q = 0; q < QH; q++) {
-            t.BoT[d * QH + q] = 0.5 * (Bm(q, d) - Bm(Q - 1 - q, d));
-            t.GoT[d * QH + q] = 0.5 * (Gm(q, d) - Gm(Q - 1 - q, d));
+            t.BoT[d * RS + q] = 0.5 * (Bm(q, d) - Bm(Q - 1 - q, d));
+            t.GoT[d * RS + q] = 0.5 * (Gm(q, d) - Gm(Q - 1 - q, d));
         }
     }
     for (int i = 1; i < LPF_TAB_COPIES; i++) tabs[i] = tabs[0];

@@ -193,7 +193,7 @@ int apply_full(lpf_ctx *c, bool constrained, const double *x, double *y, double 
 // 1 = in the last CTA of the element kernel, 2 = inside the element kernel, overlapped with the interior elements.
 int tail_mode(const lpf_ctx *c)
 {
-    if (c->nranks == 1 || !c->p2p_on || c->ess_general || c->deterministic || c->halo.n_nbr > 32) return 0;
+    if (c->nranks == 1 || !c->p2p_on || c->ess_general || c->deterministic || c->variant != 0 || c->halo.n_nbr > 32) return 0;
     if (c->p2p_fuse == 1) return (c->halo.n_nbr > 0 && c->halo.total <= c->p2p_fuse_max) ? 1 : 0;
     return c->p2p_fuse == 2 ? 2 : 0;
 }

@@ -21,17 +21,18 @@ __device__ __forceinline__ void eo_contract(const double *__restrict__ Me, const
                                             double (&out)[NO])
 {
     constexpr int NIC = (NI + 1) / 2, NIH = NI / 2, NOC = (NO + 1) / 2, NOH = NO / 2;
+    constexpr int RS = ((((NI > NO ? NI : NO) + 1) / 2) + 1) & ~1;      // row stride of the half tables: LpfOrderTab::RS
 #pragma unroll
     for (int j = 0; j < NOC; j++) {
         const bool mid = (j >= NOH);                  // middle output row (NO odd): only one parity survives
         double se = 0.0, so = 0.0;
         if (!(mid && SIGN < 0)) {
 #pragma unroll
-            for (int i = 0; i < NIC; i++) se = fma(Me[j * NIC + i], e[i], se);
+            for (int i = 0; i < NIC; i++) se = fma(Me[j * RS + i], e[i], se);
         }
         if (!(mid && SIGN > 0)) {
 #pragma unroll
-            for (int i = 0; i < NIH; i++) so = fma(Mo[j * NIH + i], o[i], so);
+            for (int i = 0; i < NIH; i++) so = fma(Mo[j * RS + i], o[i], so);
         }
         if (ACC) out[j] += se + so; else out[j] = se + so;
         if (!mid) {

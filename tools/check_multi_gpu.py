@@ -89,6 +89,21 @@ def run_checks(lpf, world, rank, local, stream, comm="p2p", order=4, mesh_kind="
     dist.all_reduce(glob)
     check("shared copies bit-identical", float((glob[l2g] - yl).abs().max()), 1e-300)
 
+    # T-vectors <-> L-vectors (lpf_prolong / lpf_restrict, what the MFEM adapter uses): the true dofs of all ranks partition the
+    # global dofs; P of the owned values reproduces every copy; R P = identity
+    nt = ctx.ntrue(0)
+    cnt = torch.tensor([float(nt)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(cnt)
+    check("sum of true dofs - global dofs", abs(float(cnt[0]) - ssp.ndof), 0.5)
+    owned_idx = torch.from_numpy(np.nonzero(sp.owned)[0].astype(np.int64)).cuda()
+    xT = xl[owned_idx].contiguous() if nt else torch.zeros(1, dtype=torch.float64, device="cuda")
+    xL2 = torch.full_like(xl, float("nan"))
+    ctx.prolong(xT, xL2)
+    check("prolong: P x_T == consistent L-vector", float((xL2 - xl).abs().max()), 1e-300)
+    xT2 = torch.full_like(xT, float("nan"))
+    ctx.restrict(xL2, xT2)
+    check("restrict: R P x_T == x_T", float((xT2 - xT).abs().max()) if nt else 0.0, 1e-300)
+
     # Laplace solve from Airy Dirichlet data
     w = lpf.wave_params()
     xyz = ssp.node_coordinates()

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "master-thesis-lpf-in-mfem_b200", "build")
 OPS = ["DFMA", "DADD", "DMUL", "DMMA", "LDCU", "LDC", "R2UR", "UBLKCP", "SYNCS", "REDG", "ATOMG", "LDS", "STS", "BAR", "LDL", "STL"]
 # (E, MINB) of the default stored-q-data kernel per order (apply_order.cu launch_default)
-DEFAULT = {1: (16, 3), 2: (8, 3), 3: (8, 2), 4: (3, 3), 5: (3, 2), 6: (2, 3), 7: (1, 3), 8: (1, 2), 9: (1, 1), 10: (1, 1)}
+DEFAULT = {1: (16, 3), 2: (8, 3), 3: (8, 2), 4: (3, 4), 5: (3, 2), 6: (2, 3), 7: (1, 3), 8: (1, 2), 9: (1, 1), 10: (1, 1)}
 
 
 def kernels(obj):

@@ -26,34 +26,54 @@ __host__ __device__ constexpr int lpf_smem_stride(int p, int which)
     return T[p][which];
 }
 
-template <int P, int E>
+// Aliased layout (LAY = 1, round 2): the A buffer lives INSIDE the B buffer, A[k][dz][dy][qx] = B[k][dz][qy = dy][qx].  The
+// shared-memory words a Y-stage thread (dz, qx) reads from A (2 D of them) are then a subset of the words it writes to B
+// (3 Q) -- and the other way round in the Yt stage -- so every thread overwrites only what it has itself read before, no
+// extra barrier is needed and the A buffer's 2 D SAZ doubles per element disappear: 28.5 -> 17.1 KB at order 7 (four CTAs
+// per SM instead of three), 35.9 -> 22.9 KB at order 8 (three instead of two).  B rows get their own stride SBY >= Q (odd
+// where Q is even, or the X stage's row stores collide).  {SBY, SBZ, PAD} from tools/smem_layout_sim.py <p> <E> alias:
+// wavefronts per element p4 322, p5 525, p6 810, p7 1006, p8 1394 (separate buffers: 322 / 496 / 642 / 862 / 1394).
+__host__ __device__ constexpr int lpf_smem_alias(int p, int which)
+{
+    constexpr int T[11][3] = {{0, 0, 0}, {3, 9, 0}, {4, 16, 0}, {5, 28, 9}, {7, 54, 4}, {7, 55, 12}, {9, 72, 0},
+                              {9, 89, 0}, {10, 106, 0}, {11, 123, 0}, {13, 156, 0}};
+    return T[p][which];
+}
+// the layout the tuned kernel of an order uses (apply_order.cu launch_default)
+__host__ __device__ constexpr int lpf_default_layout(int p) { return p >= 6 ? 1 : 0; }
+
+template <int P, int E, int LAY = 0>
 struct ApplyCfg {
     static constexpr int D = P + 1, Q = P + 2;
     static constexpr int LX = D * D, LY = D * Q, LZ = Q * Q;
     static constexpr int NT = E * LZ;
     static constexpr int D3 = D * D * D;
     static constexpr int DP3 = (D * D * D + 3) & ~3;    // gather-map row stride (rows padded to 16 bytes for bulk copies)
-    static constexpr int SAY = lpf_smem_stride(P, 0);
-    static constexpr int SAZ = lpf_smem_stride(P, 1);
-    static constexpr int SAA = D * SAZ;
-    static constexpr int SBZ = lpf_smem_stride(P, 2);
+    static constexpr bool ALIAS = LAY == 1;
+    static constexpr int SBY = ALIAS ? lpf_smem_alias(P, 0) : Q;               // B = [arr 3][dz][qy][qx], strides SBA, SBZ, SBY, 1
+    static constexpr int SBZ = ALIAS ? lpf_smem_alias(P, 1) : lpf_smem_stride(P, 2);
     static constexpr int SBA = D * SBZ;
-    static constexpr int ES = 2 * SAA + 3 * SBA + lpf_smem_stride(P, 3);      // element stride
-    static constexpr int OFFB = 2 * SAA;
+    static constexpr int SAY = ALIAS ? SBY : lpf_smem_stride(P, 0);            // A = [arr 2][dz][dy][qx], strides SAA, SAZ, SAY, 1
+    static constexpr int SAZ = ALIAS ? SBZ : lpf_smem_stride(P, 1);
+    static constexpr int SAA = ALIAS ? SBA : D * SAZ;
+    static constexpr int OFFB = ALIAS ? 0 : 2 * SAA;
+    static constexpr int ES = (ALIAS ? 3 * SBA + lpf_smem_alias(P, 2) : 2 * SAA + 3 * SBA + lpf_smem_stride(P, 3));      // element stride
     static constexpr size_t SMEM_BYTES = (size_t)E * ES * sizeof(double);
-    static_assert(SAY >= Q && SAZ >= D * SAY - (SAY - Q) && SBZ >= Q * Q, "stage-buffer strides too small");
+    static_assert(SAY >= Q && SAZ >= D * SAY - (SAY - Q) && SBZ >= Q * SBY - (SBY - Q), "stage-buffer strides too small");
+    // Z-stage column (qy, qx) of thread q2 = qy Q + qx inside a B slab
+    __device__ static __forceinline__ int zcol(int q2) { if constexpr (SBY == Q) return q2; else return (q2 / Q) * SBY + (q2 % Q); }
 };
 
-template <int P, int E, bool AFF = false>      // AFF: affine fast path, no q-data staging area (pa_apply_eo.cuh)
-struct TmaCfg : ApplyCfg<P, E> {
-    using B = ApplyCfg<P, E>;
+template <int P, int E, bool AFF = false, int LAY = 0>      // AFF: affine fast path, no q-data staging area (pa_apply_eo.cuh)
+struct TmaCfg : ApplyCfg<P, E, LAY> {
+    using B = ApplyCfg<P, E, LAY>;
     static constexpr int QE = 6 * B::Q * B::Q * B::Q;               // doubles of q-data per element
     // byte offsets inside dynamic shared memory
     static constexpr size_t OFF_Q = 0;                                                  // [E][QE] doubles (16B aligned)
     static constexpr size_t OFF_IDX = OFF_Q + (AFF ? (size_t)0 : (size_t)E * QE * 8);   // [2][E][DP3] ints
     static constexpr size_t OFF_WORK = (OFF_IDX + (size_t)2 * E * B::DP3 * 4 + 15) & ~(size_t)15;
-    static constexpr size_t OFF_BAR = (OFF_WORK + (size_t)E * B::ES * 8 + 15) & ~(size_t)15;   // 3 mbarriers
-    static constexpr size_t SMEM_BYTES = OFF_BAR + 64;
+    static constexpr size_t OFF_BAR = (OFF_WORK + (size_t)E * B::ES * 8 + 15) & ~(size_t)15;   // 3 mbarriers + the q-data release counter
+    static constexpr size_t SMEM_BYTES = OFF_BAR + 32;
 };
 
 // ---- per-order coefficient tables ----------------------------------------------------------------------------------

@@ -21,18 +21,19 @@ constexpr int P = LPF_ORDER;
 // TABS < 0: the order's default (one coefficient-table copy per stage from order 7 up, from order 6 up in the kernels that
 // carry the overlapped halo exchange -- the variants where ptxas otherwise falls back to per-thread LDC loads,
 // profiles/r02_sass_opcodes.md)
-template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1, bool WOVL = false>
+template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1, bool WOVL = false, int LAY = 0, int EQ = 0>
 int launch_persistent(LpfApplyArgs &a)
 {
-    using C = TmaCfg<P, E, AFF>;
+    using C = TmaCfg<P, E, AFF, LAY>;
+    static_assert(EO || (LAY == 0 && EQ == 0), "layout / early-release options exist in the even-odd kernel only");
     constexpr int TS = TABS >= 0 ? TABS : (P >= 7 ? 1 : 0), TSO = TABS >= 0 ? TABS : (P >= 6 ? 1 : 0);
     static int blocks_per_sm[2][16] = {{0}};
     // WOVL: also instantiate the kernels that carry the multi-GPU exchange hooks (tuned default and affine kernels only; the
     // alternative variants of the tuning sweep exchange through the separate LL kernel, lpf_device.cu tail_mode)
     void (*kd)(const ApplyKArgs), (*kn)(const ApplyKArgs), (*kod)(const ApplyKArgs) = nullptr, (*kon)(const ApplyKArgs) = nullptr;
     if constexpr (EO) {
-        kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, false, TS>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, false, TS>;
-        if constexpr (WOVL) { kod = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, true, TSO>; kon = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, true, TSO>; }
+        kd = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, false, TS, LAY, EQ>; kn = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, false, TS, LAY, EQ>;
+        if constexpr (WOVL) { kod = pa_apply_eo_kernel<P, E, true, MINB, AFF, DET, true, TSO, LAY, EQ>; kon = pa_apply_eo_kernel<P, E, false, MINB, AFF, DET, true, TSO, LAY, EQ>; }
     } else {
         kd = pa_apply_tma_kernel<P, E, true, MINB, DET, false>; kn = pa_apply_tma_kernel<P, E, false, MINB, DET, false>;
         if constexpr (WOVL) { kod = pa_apply_tma_kernel<P, E, true, MINB, DET, true>; kon = pa_apply_tma_kernel<P, E, false, MINB, DET, true>; }
@@ -48,7 +49,7 @@ int launch_persistent(LpfApplyArgs &a)
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, ovl ? kod : kd, C::NT, C::SMEM_BYTES));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ovl ? kon : kn, C::NT, C::SMEM_BYTES));
         bps = std::max(1, std::min(b0, b1));
-        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d ovl=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, (int)ovl, C::NT, (size_t)C::SMEM_BYTES, bps);
+        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d lay=%d eq=%d ovl=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, LAY, EQ, (int)ovl, C::NT, (size_t)C::SMEM_BYTES, bps);
     }
     const int nb = (a.k.ne + E - 1) / E;
     a.threads = C::NT; a.smem = C::SMEM_BYTES; a.grid = 0;
@@ -82,8 +83,11 @@ int launch_default(LpfApplyArgs &a)
         else if constexpr (P == 4) return launch_persistent<3, 4, true, false, DET, -1, !DET>(a);
         else if constexpr (P == 5) return launch_persistent<3, 2, true, false, DET, -1, !DET>(a);
         else if constexpr (P == 6) return launch_persistent<2, 3, true, false, DET, -1, !DET>(a);
-        else if constexpr (P == 7) return launch_persistent<1, 3, true, false, DET, -1, !DET>(a);
-        else if constexpr (P == 8) return launch_persistent<1, 2, true, false, DET, -1, !DET>(a);
+        // orders 7-9: stage buffers aliased (A inside B, apply_cfg.cuh) -> 4 / 3 / 2 CTAs per SM instead of 3 / 2 / 1;
+        // order 7 also releases the q-data buffer early (the only order where that measured faster, profiles/r02_sweep_orders.txt)
+        else if constexpr (P == 7) return launch_persistent<1, 4, true, false, DET, -1, !DET, 1, 1>(a);
+        else if constexpr (P == 8) return launch_persistent<1, 3, true, false, DET, -1, !DET, 1, 0>(a);
+        else if constexpr (P == 9) return launch_persistent<1, 2, true, false, DET, -1, !DET, 1, 0>(a);
         else return launch_persistent<1, 1, true, false, DET, -1, !DET>(a);
     }
 }
@@ -114,9 +118,26 @@ int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
         else if constexpr (P == 4) return launch_persistent<2, 5, true>(a);
         else if constexpr (P == 5) return launch_persistent<2, 3, true>(a);
         else if constexpr (P == 6) return launch_persistent<2, 2, true, false, false, 1>(a);
-        else if constexpr (P == 7) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<1, 2, true>(a); }
-        else if constexpr (P == 8) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<2, 1, true>(a); }
+        else if constexpr (P == 7) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<1, 3, true>(a); }
+        else if constexpr (P == 8) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<1, 2, true>(a); }
         else return launch_default<false, false>(a);
+    }
+    if (v >= 40 && v < 50) {      // round-2 experiments: aliased stage buffers (LAY = 1); EQ bit 0 = early q-data release, bit 1 = no proxy fences
+        // 40: aliased; 41: + early release; 42: + early release, no fences; 43: aliased, no fences; 44: old layout, no fences; 45: old layout, early release, no fences
+#define LPF_EXP(E_, M_, T_)                                                                              \
+        if (v == 40) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 0>(a);           \
+        if (v == 41) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 1>(a);           \
+        if (v == 42) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 3>(a);           \
+        if (v == 43) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 2>(a);
+        if constexpr (P < 4) return launch_default<false, false>(a);
+        else if constexpr (P == 4) { LPF_EXP(3, 4, -1) if (v == 44) return launch_persistent<3, 4, true, false, false, -1, false, 0, 2>(a); return launch_persistent<3, 4, true, false, false, -1, false, 0, 3>(a); }
+        else if constexpr (P == 5) { LPF_EXP(3, 2, -1) if (v == 44) return launch_persistent<3, 2, true, false, false, -1, false, 0, 2>(a); return launch_persistent<3, 2, true, false, false, -1, false, 0, 3>(a); }
+        else if constexpr (P == 6) { LPF_EXP(2, 2, 1) if (v == 44) return launch_persistent<2, 3, true, false, false, -1, false, 0, 2>(a); return launch_persistent<2, 3, true, false, false, -1, false, 0, 3>(a); }
+        else if constexpr (P == 7) { LPF_EXP(1, 4, 1) if (v == 44) return launch_persistent<1, 3, true, false, false, -1, false, 0, 2>(a); return launch_persistent<1, 3, true, false, false, -1, false, 0, 3>(a); }
+        else if constexpr (P == 8) { LPF_EXP(1, 3, 1) if (v == 44) return launch_persistent<1, 2, true, false, false, -1, false, 0, 2>(a); return launch_persistent<1, 2, true, false, false, -1, false, 0, 3>(a); }
+        else if constexpr (P == 9) { LPF_EXP(1, 2, 1) return launch_persistent<1, 1, true, false, false, -1, false, 0, 3>(a); }
+        else { LPF_EXP(1, 1, 1) return launch_persistent<1, 1, true, false, false, -1, false, 0, 3>(a); }
+#undef LPF_EXP
     }
     lpf::set_error("unknown apply_variant " + std::to_string(v));
     return LPF_ERR_ARG;

@@ -74,17 +74,18 @@ __device__ __forceinline__ double p2p_recv_entry(const P2PPlanDev &h, const uint
 // into the neighbours' mailboxes, waits for theirs, adds the partial sums in rank order and all-reduces the PCG
 // denominator -- the collective rides on the compute kernel, no extra launch, no NCCL.  One CTA works through the whole
 // interface, so this pays only for small interfaces (option p2p_fuse = 1).
-__device__ __forceinline__ void p2p_apply_tail_last(const P2PTail &t, double *__restrict__ y)
+// (sflag: one int of the caller's dynamic shared memory -- the apply kernels keep their static shared memory at zero, the
+// order-8 CTA fills its third of the SM to within a few bytes)
+__device__ __forceinline__ void p2p_apply_tail_last(const P2PTail &t, double *__restrict__ y, volatile int *sflag)
 {
-    __shared__ bool tail_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int n = atomicInc(t.done, gridDim.x - 1);
-        tail_last = (n == gridDim.x - 1);
+        *sflag = (n == gridDim.x - 1);
     }
     __syncthreads();
-    if (!tail_last) return;
+    if (!*sflag) return;
     __threadfence();
     const int tid = threadIdx.x, nt = blockDim.x;
     const P2PPlanDev &h = t.h;
@@ -156,7 +157,7 @@ __device__ __forceinline__ void p2p_if_try_send(const P2PTail &t, P2POverlap &o,
     if (o.sent) return;
     if (*(volatile unsigned int *)&t.d.local->if_done >= (unsigned int)t.n_if_batches) p2p_if_send_share(t, o, y);
 }
-__device__ __forceinline__ void p2p_if_finish(const P2PTail &t, P2POverlap &o, double *__restrict__ y)
+__device__ __forceinline__ void p2p_if_finish(const P2PTail &t, P2POverlap &o, double *__restrict__ y, volatile int *sflag)
 {
     if (!o.sent) {                         // few batches per CTA: the interface may still be in flight on other CTAs
         long long n = 0;
@@ -171,15 +172,14 @@ __device__ __forceinline__ void p2p_if_finish(const P2PTail &t, P2POverlap &o, d
         const int dof = t.h.shared[i];
         y[dof] = p2p_recv_entry(t.h, recv, o.flag, i, __ldcg(y + dof), &t.d.local->error);
     }
-    __shared__ bool tail_last;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int n = atomicInc(t.done, gridDim.x - 1);
-        tail_last = (n == gridDim.x - 1);
+        *sflag = (n == gridDim.x - 1);
     }
     __syncthreads();
-    if (!tail_last) return;
+    if (!*sflag) return;
     __threadfence();
     if (t.with_den && threadIdx.x < 32) {
         double s = 0.0;

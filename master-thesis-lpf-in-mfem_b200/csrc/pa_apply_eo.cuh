@@ -55,11 +55,22 @@ __device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N +
 // 87 % of the kernel's HBM bytes at order 4 -- disappears and the kernel becomes FP64-issue-bound.  Used automatically
 // when every element of the mesh is affine (all wave tanks of the reference); reported separately from the graded
 // stored-q-data number.
-template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false, bool OVL = false, int TABS = 0>
+// LAY: stage-buffer layout (apply_cfg.cuh; 1 = A buffer aliased into the B buffer).
+// EQ: early release of the q-data buffer.  The buffer is dead as soon as every thread has multiplied its column by the D
+// tensor -- before the backward z contraction, a third of the Z stage -- so the warps count themselves out on a shared-memory
+// counter and the LAST one issues the bulk copy of the next batch's q-data right there instead of behind the stage barrier:
+// the copy is in flight for a larger part of the batch (one q-data buffer per CTA is all that fits at orders 7, 8).
+template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false, bool OVL = false, int TABS = 0, int LAY = 0, int EQ = 0>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
 pa_apply_eo_kernel(const ApplyKArgs ka)
 {
-    using C = TmaCfg<P, E, AFF>;
+    using C = TmaCfg<P, E, AFF, LAY>;
+    constexpr bool EQR = (EQ & 1) && !AFF;
+    // EQ & 2: no fence.proxy.async before a refill.  The fence (SASS MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) orders generic-proxy
+    // WRITES before the async proxy; the q-data and gather-map buffers are only ever READ by the threads, and those reads are
+    // ordered before the refill by the barrier (or the release counter) the issuing thread has passed -- the same
+    // write-after-read hand-over as in any TMA load pipeline (consumer arrives on a barrier, producer issues the copy).
+    constexpr bool NOFENCE = (EQ & 2) != 0;
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
     constexpr int DP3 = C::DP3, QE = C::QE, D3 = C::D3;
     const double *__restrict__ qd = ka.qd;
@@ -74,6 +85,8 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
     double *smem = reinterpret_cast<double *>(smem_raw + C::OFF_WORK);
     uint64_t *bar_q = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
     uint64_t *bar_i = bar_q + 1;
+    uint32_t *qcnt = reinterpret_cast<uint32_t *>(bar_q + 3);      // EQ: warps that are done with the q-data buffer
+    volatile int *sflag = reinterpret_cast<volatile int *>(qcnt + 1);      // "this CTA finished last" (multi-GPU tails)
 
     const int tid = threadIdx.x;
     const int nb = (ne + E - 1) / E;
@@ -88,6 +101,7 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
 
     if (tid == 0) {
         mbar_init(bar_q, 1); mbar_init(bar_i, 1); mbar_init(bar_i + 1, 1);
+        *qcnt = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -161,7 +175,7 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         // gather map of the next batch (issued behind the first barrier after the previous batch's Xt stage, pa_apply_tma.cuh)
         if (tid == 0 && has_next) {
             const int n1 = batch_elems(bn);
-            fence_proxy_async();
+            if (!NOFENCE) fence_proxy_async();
             mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
             bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
         }
@@ -180,16 +194,16 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
             eo_contract<D, Q, +1, false>(TY.BeF, TY.BoF, e, o, s2);      // B_y G_x u
             double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
 #pragma unroll
-            for (int q = 0; q < Q; q++) { bb[q * Q] = s0[q]; bb[C::SBA + q * Q] = s1[q]; bb[2 * C::SBA + q * Q] = s2[q]; }
+            for (int q = 0; q < Q; q++) { bb[q * C::SBY] = s0[q]; bb[C::SBA + q * C::SBY] = s1[q]; bb[2 * C::SBA + q * C::SBY] = s2[q]; }
         }
         __syncthreads();
 
         // ---- Z stage: column (qy,qx): forward z for all levels, D tensor per level, backward z ----
         if (!AFF) mbar_wait(bar_q, it & 1);
+        double *bb = smem + ez * C::ES + C::OFFB + C::zcol(q2);
+        double g0[Q], g1[Q], g2[Q];
         if (zvalid) {
-            double *bb = smem + ez * C::ES + C::OFFB + q2;
             const double2 *sqv = reinterpret_cast<const double2 *>(sq) + (size_t)ez * (QE / 2) + q2;
-            double g0[Q], g1[Q], g2[Q];
             {
                 double u[D], e[DC], o[DH];
 #pragma unroll
@@ -226,6 +240,29 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
                     g2[qz] = d1.x * a0 + d2.x * a1 + d2.y * a2;
                 }
             }
+        }
+        if (EQR) {      // this warp is done with the q-data buffer; the last warp to say so refills it
+            constexpr int NW = (C::NT + 31) / 32;
+            const int wbase = tid & ~31, live = C::NT - wbase;
+            __syncwarp(live >= 32 ? 0xffffffffu : ((1u << live) - 1u));
+            if ((tid & 31) == 0) {
+                uint32_t old;
+                // relaxed on purpose: an acq_rel atomic costs a MEMBAR.ALL.CTA that also waits for the scatter REDs still in
+                // flight (measured: -9 % at order 8).  Ordering comes from the shared-memory pipeline itself: a warp's LDS of
+                // the q-data are processed before its own ATOMS, so whoever reads NW - 1 here knows every read is done.
+                asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(qcnt)) : "memory");
+                if (old == NW - 1) {
+                    *qcnt = 0;      // next increment: behind at least one CTA-wide barrier
+                    if (has_next) {
+                        const int n1 = batch_elems(bn);
+                        if (!NOFENCE) fence_proxy_async();
+                        mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
+                        bulk_g2s_stream(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q, l2pol);
+                    }
+                }
+            }
+        }
+        if (zvalid) {
             {
                 double c[D], e[QC], o[QH];
                 eo_split<Q>(g0, e, o);
@@ -244,9 +281,9 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         }
         __syncthreads();
 
-        if (!AFF && tid == 0 && has_next) {
+        if (!AFF && !EQR && tid == 0 && has_next) {
             const int n1 = batch_elems(bn);
-            fence_proxy_async();
+            if (!NOFENCE) fence_proxy_async();
             mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
             bulk_g2s_stream(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q, l2pol);
         }
@@ -262,15 +299,15 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
             const double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
             double v[Q], e[QC], o[QH], ta[D], tb[D];
 #pragma unroll
-            for (int q = 0; q < Q; q++) v[q] = bb[q * Q];
+            for (int q = 0; q < Q; q++) v[q] = bb[q * C::SBY];
             eo_split<Q>(v, e, o);
             eo_contract<Q, D, +1, false>(TYt.BeT, TYt.BoT, e, o, ta);
 #pragma unroll
-            for (int q = 0; q < Q; q++) v[q] = bb[C::SBA + q * Q];
+            for (int q = 0; q < Q; q++) v[q] = bb[C::SBA + q * C::SBY];
             eo_split<Q>(v, e, o);
             eo_contract<Q, D, -1, true>(TYt.GeT, TYt.GoT, e, o, ta);
 #pragma unroll
-            for (int q = 0; q < Q; q++) v[q] = bb[2 * C::SBA + q * Q];
+            for (int q = 0; q < Q; q++) v[q] = bb[2 * C::SBA + q * C::SBY];
             eo_split<Q>(v, e, o);
             eo_contract<Q, D, +1, false>(TYt.BeT, TYt.BoT, e, o, tb);
             double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
@@ -309,8 +346,8 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         apply_batch_end<OVL>(ka.tail, ov, b, y);
     }
 
-    if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots);
+    if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots, smem);
     // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, riding on this kernel
-    if (OVL && ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
-    else if (OVL && ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
+    if (OVL && ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y, sflag);
+    else if (OVL && ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y, sflag);
 }

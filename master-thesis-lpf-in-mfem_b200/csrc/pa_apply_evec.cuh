@@ -75,16 +75,16 @@ pa_apply_evec_kernel(const double *__restrict__ qd, const double *__restrict__ x
                 s1 = fma(T.BG[2 * (q * D + i) + 1], ua[i], s1);     // G_y B_x u
                 s2 = fma(T.BG[2 * (q * D + i)], ub[i], s2);     // B_y G_x u
             }
-            b[q * Q] = s0;
-            b[C::SBA + q * Q] = s1;
-            b[2 * C::SBA + q * Q] = s2;
+            b[q * C::SBY] = s0;
+            b[C::SBA + q * C::SBY] = s1;
+            b[2 * C::SBA + q * C::SBY] = s2;
         }
     }
     __syncthreads();
 
     // ---- Z stage: column (qy,qx): forward z, q-data, backward z, all in registers ----
     if (zvalid) {
-        double *b = smem + ez * C::ES + C::OFFB + q2;
+        double *b = smem + ez * C::ES + C::OFFB + C::zcol(q2);
         double ubb[D], ubg[D], ugb[D], cbb[D], cbg[D], cgb[D];
 #pragma unroll
         for (int i = 0; i < D; i++) {
@@ -130,7 +130,7 @@ pa_apply_evec_kernel(const double *__restrict__ qd, const double *__restrict__ x
         const double *b = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
         double vbb[Q], vbg[Q], vgb[Q];
 #pragma unroll
-        for (int q = 0; q < Q; q++) { vbb[q] = b[q * Q]; vbg[q] = b[C::SBA + q * Q]; vgb[q] = b[2 * C::SBA + q * Q]; }
+        for (int q = 0; q < Q; q++) { vbb[q] = b[q * C::SBY]; vbg[q] = b[C::SBA + q * C::SBY]; vgb[q] = b[2 * C::SBA + q * C::SBY]; }
         double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
 #pragma unroll
         for (int i = 0; i < D; i++) {

@@ -26,12 +26,14 @@
 
 // ---- pieces shared by the persistent kernels ----
 // x_e . y_e partial of this CTA -> its (d, A d) slot (one slot per CTA: grids are capped at LPF_DEN_SLOTS)
+// (wsum: the stage buffers, free after the last batch -- no static shared memory, the order-8 CTA fills its third of the SM
+// to within a few bytes)
 template <int NT>
-__device__ __forceinline__ void apply_den_epilogue(double part, double *__restrict__ den_slots)
+__device__ __forceinline__ void apply_den_epilogue(double part, double *__restrict__ den_slots, double *wsum)
 {
     part = warp_sum_partial(part, NT);
-    __shared__ double wsum[32];
     const int tid = threadIdx.x, w = tid >> 5, nw = (NT + 31) >> 5;
+    __syncthreads();      // every thread is done with the stage buffers
     if ((tid & 31) == 0) wsum[w] = part;
     __syncthreads();
     if (tid == 0) {
@@ -73,6 +75,7 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
     double *smem = reinterpret_cast<double *>(smem_raw + C::OFF_WORK);
     uint64_t *bar_q = reinterpret_cast<uint64_t *>(smem_raw + C::OFF_BAR);
     uint64_t *bar_i = bar_q + 1;      // two of them
+    volatile int *sflag = reinterpret_cast<volatile int *>(bar_q + 3) + 1;      // "this CTA finished last" (multi-GPU tails)
     const double *__restrict__ qd = ka.qd;
     const int *__restrict__ gmap = ka.gmap;
     const double *__restrict__ x = ka.x;
@@ -185,9 +188,9 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
                     s1 = fma(c.y, ua[i], s1);
                     s2 = fma(c.x, ub[i], s2);
                 }
-                bb[q * Q] = s0;
-                bb[C::SBA + q * Q] = s1;
-                bb[2 * C::SBA + q * Q] = s2;
+                bb[q * C::SBY] = s0;
+                bb[C::SBA + q * C::SBY] = s1;
+                bb[2 * C::SBA + q * C::SBY] = s2;
             }
         }
         __syncthreads();
@@ -195,7 +198,7 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
         // ---- Z stage: q-data from shared memory ----
         mbar_wait(bar_q, it & 1);
         if (zvalid) {
-            double *bb = smem + ez * C::ES + C::OFFB + q2;
+            double *bb = smem + ez * C::ES + C::OFFB + C::zcol(q2);
             const double2 *sqv = reinterpret_cast<const double2 *>(sq) + (size_t)ez * (QE / 2) + q2;
             double ubb[D], ubg[D], ugb[D], cbb[D], cbg[D], cgb[D];
 #pragma unroll
@@ -252,7 +255,7 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
             const double *bb = smem + ey * C::ES + C::OFFB + ydz * C::SBZ + yqx;
             double vbb[Q], vbg[Q], vgb[Q];
 #pragma unroll
-            for (int q = 0; q < Q; q++) { vbb[q] = bb[q * Q]; vbg[q] = bb[C::SBA + q * Q]; vgb[q] = bb[2 * C::SBA + q * Q]; }
+            for (int q = 0; q < Q; q++) { vbb[q] = bb[q * C::SBY]; vbg[q] = bb[C::SBA + q * C::SBY]; vgb[q] = bb[2 * C::SBA + q * C::SBY]; }
             double *a = smem + ey * C::ES + ydz * C::SAZ + yqx;
 #pragma unroll
             for (int i = 0; i < D; i++) {
@@ -298,8 +301,8 @@ pa_apply_tma_kernel(const ApplyKArgs ka)
 #undef BGL
     }
 
-    if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots);
+    if (DEN && ka.den_slots != nullptr) apply_den_epilogue<C::NT>(part, ka.den_slots, smem);
     // multi-GPU: halo-sum (+ PCG denominator all-reduce) over NVLink peer memory, riding on this kernel
-    if (OVL && ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y);
-    else if (OVL && ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y);
+    if (OVL && ka.tail.mode == 1) p2p_apply_tail_last(ka.tail, y, sflag);
+    else if (OVL && ka.tail.mode == 2) p2p_if_finish(ka.tail, ov, y, sflag);
 }

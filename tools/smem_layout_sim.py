@@ -23,13 +23,18 @@ def wavefronts(addrs):
     return tot
 
 
-def simulate(P, E, SAY, SAZ, SBZ, ES_pad):
+def simulate(P, E, SAY, SAZ, SBZ, ES_pad, alias=False):
+    """alias: the A buffer lives INSIDE the B buffer (A[k][dz][dy][qx] = B[k][dz][qy = dy][qx], round 2): SAY = Q, SAZ = SBZ."""
     D, Q = P + 1, P + 2
     LX, LY, LZ = D * D, D * Q, Q * Q
     NT = E * LZ
     SAA, SBA = D * SAZ, D * SBZ
     ES = (2 * SAA + 3 * SBA) + ES_pad
     OFFB = 2 * SAA
+    if alias:
+        assert SAY == Q and SAZ == SBZ
+        ES = 3 * SBA + ES_pad
+        OFFB = 0
     total, ideal = 0, 0
 
     def run(instrs):
@@ -90,6 +95,16 @@ def simulate(P, E, SAY, SAZ, SBZ, ES_pad):
 if __name__ == "__main__":
     P, E = int(sys.argv[1]), int(sys.argv[2])
     D, Q = P + 1, P + 2
+    if len(sys.argv) > 3 and sys.argv[3] == "alias":      # aliased layout: search (SBZ, pad) only
+        best = []
+        for SBZ in range(Q * Q, Q * Q + 33):
+            for pad in range(0, 16):
+                r = simulate(P, E, Q, SBZ, SBZ, pad, alias=True)
+                best.append((r["per_elem"], r["smem_bytes"], Q, SBZ, SBZ, pad, r["x"], r["y"], r["z"]))
+        best.sort()
+        for b in best[:10]:
+            print(b)
+        sys.exit(0)
     def pad_to(v, m):
         while v % 16 != m % 16: v += 1
         return v

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--refine-high", type=int, default=1, help="refinements for orders >= 5")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--out", default="")
+    ap.add_argument("--verbose", action="store_true", help="print the launch geometry (threads, shared memory, CTAs/SM) of every kernel variant")
     a = ap.parse_args()
     lpf = importlib.import_module("master-thesis-lpf-in-mfem_b200")
     torch.cuda.set_device(0)
@@ -36,6 +37,8 @@ def main():
         ctx = lpf.Context(sp, device=0, stream=torch.cuda.current_stream().cuda_stream)
         ctx.pa_setup()
         ctx.set_option("affine", 0)          # the general stored-q-data kernels
+        if a.verbose:
+            ctx.set_option("verbose", 1)
         x = torch.rand(sp.ndof, dtype=torch.float64, device="cuda") - 0.5
         y = torch.empty_like(x)
         D, Q = p + 1, p + 2

@@ -32,7 +32,9 @@ __host__ __device__ constexpr int lpf_smem_stride(int p, int which)
 // extra barrier is needed and the A buffer's 2 D SAZ doubles per element disappear: 28.5 -> 17.1 KB at order 7 (four CTAs
 // per SM instead of three), 35.9 -> 22.9 KB at order 8 (three instead of two).  B rows get their own stride SBY >= Q (odd
 // where Q is even, or the X stage's row stores collide).  {SBY, SBZ, PAD} from tools/smem_layout_sim.py <p> <E> alias:
-// wavefronts per element p4 322, p5 525, p6 810, p7 1006, p8 1394 (separate buffers: 322 / 496 / 642 / 862 / 1394).
+// wavefronts per element p4 322, p5 525, p6 810, p7 1006, p8 1394 (separate buffers: 322 / 496 / 642 / 862 / 1394).  Measured
+// (profiles/r02_sweep_orders.txt): orders 7 / 8 / 9 gain 10-60 %; orders 4-6 lose 5-13 % (same CTAs per SM, more conflicts --
+// order 6 even with the most compact variant that fits three CTAs per SM), so they keep separate buffers.
 __host__ __device__ constexpr int lpf_smem_alias(int p, int which)
 {
     constexpr int T[11][3] = {{0, 0, 0}, {3, 9, 0}, {4, 16, 0}, {5, 28, 9}, {7, 54, 4}, {7, 55, 12}, {9, 72, 0},
@@ -40,7 +42,7 @@ __host__ __device__ constexpr int lpf_smem_alias(int p, int which)
     return T[p][which];
 }
 // the layout the tuned kernel of an order uses (apply_order.cu launch_default)
-__host__ __device__ constexpr int lpf_default_layout(int p) { return p >= 6 ? 1 : 0; }
+__host__ __device__ constexpr int lpf_default_layout(int p) { return p >= 7 && p <= 9 ? 1 : 0; }
 
 template <int P, int E, int LAY = 0>
 struct ApplyCfg {

@@ -21,11 +21,11 @@ constexpr int P = LPF_ORDER;
 // TABS < 0: the order's default (one coefficient-table copy per stage from order 7 up, from order 6 up in the kernels that
 // carry the overlapped halo exchange -- the variants where ptxas otherwise falls back to per-thread LDC loads,
 // profiles/r02_sass_opcodes.md)
-template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1, bool WOVL = false, int LAY = 0, int EQ = 0>
+template <int E, int MINB, bool EO, bool AFF = false, bool DET = false, int TABS = -1, bool WOVL = false, int LAY = 0, bool EQ = false>
 int launch_persistent(LpfApplyArgs &a)
 {
     using C = TmaCfg<P, E, AFF, LAY>;
-    static_assert(EO || (LAY == 0 && EQ == 0), "layout / early-release options exist in the even-odd kernel only");
+    static_assert(EO || (LAY == 0 && !EQ), "layout / early-release options exist in the even-odd kernel only");
     constexpr int TS = TABS >= 0 ? TABS : (P >= 7 ? 1 : 0), TSO = TABS >= 0 ? TABS : (P >= 6 ? 1 : 0);
     static int blocks_per_sm[2][16] = {{0}};
     // WOVL: also instantiate the kernels that carry the multi-GPU exchange hooks (tuned default and affine kernels only; the
@@ -49,7 +49,7 @@ int launch_persistent(LpfApplyArgs &a)
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, ovl ? kod : kd, C::NT, C::SMEM_BYTES));
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, ovl ? kon : kn, C::NT, C::SMEM_BYTES));
         bps = std::max(1, std::min(b0, b1));
-        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d lay=%d eq=%d ovl=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, LAY, EQ, (int)ovl, C::NT, (size_t)C::SMEM_BYTES, bps);
+        if (a.verbose) fprintf(stderr, "lpf: apply kernel p=%d E=%d MINB=%d eo=%d aff=%d det=%d tabs=%d/%d lay=%d eq=%d ovl=%d: %d threads, %zu B dynamic smem, %d CTAs/SM\n", P, E, MINB, (int)EO, (int)AFF, (int)DET, TS, TSO, LAY, (int)EQ, (int)ovl, C::NT, (size_t)C::SMEM_BYTES, bps);
     }
     const int nb = (a.k.ne + E - 1) / E;
     a.threads = C::NT; a.smem = C::SMEM_BYTES; a.grid = 0;
@@ -122,21 +122,15 @@ int LPF_CAT(lpf_apply_L_p, LPF_ORDER)(LpfApplyArgs &a)
         else if constexpr (P == 8) { if (v == 33) return launch_persistent<1, 2, true, false, false, 0>(a); return launch_persistent<1, 2, true>(a); }
         else return launch_default<false, false>(a);
     }
-    if (v >= 40 && v < 50) {      // round-2 experiments: aliased stage buffers (LAY = 1); EQ bit 0 = early q-data release, bit 1 = no proxy fences
-        // 40: aliased; 41: + early release; 42: + early release, no fences; 43: aliased, no fences; 44: old layout, no fences; 45: old layout, early release, no fences
-#define LPF_EXP(E_, M_, T_)                                                                              \
-        if (v == 40) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 0>(a);           \
-        if (v == 41) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 1>(a);           \
-        if (v == 42) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 3>(a);           \
-        if (v == 43) return launch_persistent<E_, M_, true, false, false, T_, false, 1, 2>(a);
-        if constexpr (P < 4) return launch_default<false, false>(a);
-        else if constexpr (P == 4) { LPF_EXP(3, 4, -1) if (v == 44) return launch_persistent<3, 4, true, false, false, -1, false, 0, 2>(a); return launch_persistent<3, 4, true, false, false, -1, false, 0, 3>(a); }
-        else if constexpr (P == 5) { LPF_EXP(3, 2, -1) if (v == 44) return launch_persistent<3, 2, true, false, false, -1, false, 0, 2>(a); return launch_persistent<3, 2, true, false, false, -1, false, 0, 3>(a); }
-        else if constexpr (P == 6) { LPF_EXP(2, 2, 1) if (v == 44) return launch_persistent<2, 3, true, false, false, -1, false, 0, 2>(a); return launch_persistent<2, 3, true, false, false, -1, false, 0, 3>(a); }
-        else if constexpr (P == 7) { LPF_EXP(1, 4, 1) if (v == 44) return launch_persistent<1, 3, true, false, false, -1, false, 0, 2>(a); return launch_persistent<1, 3, true, false, false, -1, false, 0, 3>(a); }
-        else if constexpr (P == 8) { LPF_EXP(1, 3, 1) if (v == 44) return launch_persistent<1, 2, true, false, false, -1, false, 0, 2>(a); return launch_persistent<1, 2, true, false, false, -1, false, 0, 3>(a); }
-        else if constexpr (P == 9) { LPF_EXP(1, 2, 1) return launch_persistent<1, 1, true, false, false, -1, false, 0, 3>(a); }
-        else { LPF_EXP(1, 1, 1) return launch_persistent<1, 1, true, false, false, -1, false, 0, 3>(a); }
+    if (v == 40 || v == 41) {     // the round-2 layout experiment, kept re-measurable (profiles/r02_sweep_orders.txt): stage buffer A aliased into B
+                                  // (40), plus early q-data release (41), with the (E, CTAs/SM) the smaller CTA allows
+        if constexpr (P < 5 || P > 9) return launch_default<false, false>(a);
+#define LPF_EXP(E_, M_, T_) { if (v == 40) return launch_persistent<E_, M_, true, false, false, T_, false, 1, false>(a); return launch_persistent<E_, M_, true, false, false, T_, false, 1, true>(a); }
+        else if constexpr (P == 5) LPF_EXP(3, 2, -1)
+        else if constexpr (P == 6) LPF_EXP(2, 2, 1)
+        else if constexpr (P == 7) LPF_EXP(1, 4, 1)
+        else if constexpr (P == 8) LPF_EXP(1, 3, 1)
+        else LPF_EXP(1, 2, 1)
 #undef LPF_EXP
     }
     lpf::set_error("unknown apply_variant " + std::to_string(v));

@@ -129,6 +129,12 @@ struct lpf_ctx {
     std::vector<int> hp_x_ranges_needed;       // [K] number of leading dof ranges chunk k reads
     std::vector<std::vector<int>> hp_final;    // [K] dof ranges whose y is final once chunk k is done
     std::vector<int> hp_range_end, hp_ess_end; // [R] end dof of range j, end position in the (sorted) ess list
+    // what the plan is built from (kept so that options hp_ranges / hp_chunks can rebuild it): which of 128 fine dof
+    // ranges every element touches (2 x 64-bit mask per element), the fine ranges holding shared dofs, the sorted ess list
+    int hp_R = 32, hp_K = 16, hp_fine_rs = 0;
+    std::vector<uint64_t> hp_elem_mask;
+    uint64_t hp_shared_mask[2] = {0, 0};
+    std::vector<int> hp_ess_host;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> hp_ev_x, hp_ev_c;
     cudaEvent_t hp_ev_start = nullptr, hp_ev_done = nullptr;
@@ -187,6 +193,48 @@ int apply_full(lpf_ctx *c, bool constrained, const double *x, double *y, double 
     }
     if (zero_y) CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
     return apply_launch(c, gm, x, y, den, status);
+}
+
+// Plan of the pipelined host entry point (lpf_apply_T_host): R dof ranges (R in {16, 32, 64, 128}) and K element chunks.  The
+// interior elements [n_if, ne) go first in K chunks (their dofs ascend with the element index, so chunk k only needs a
+// prefix of x), then the interface block [0, n_if) -- it reads both ends of the slab and its rows are final only after the
+// halo-sum anyway.  Chunk k needs the first hp_x_ranges_needed[k] ranges of x; range j of y is final after its
+// last-touching chunk (group K: after the halo-sum).
+void host_plan_build(lpf_ctx *c)
+{
+    c->hp_elem_begin.clear(); c->hp_elem_end.clear(); c->hp_x_ranges_needed.clear(); c->hp_final.clear();
+    c->hp_range_end.clear(); c->hp_ess_end.clear();
+    if (c->hp_elem_mask.empty()) return;
+    const int fine_per = 128 / c->hp_R;                       // fine ranges per plan range
+    const long rs = (long)c->hp_fine_rs * fine_per;
+    for (int j = 0; j < c->hp_R; j++) if (j * rs < c->ndof) c->hp_range_end.push_back((int)std::min<long>((j + 1) * rs, c->ndof));
+    const int nr = (int)c->hp_range_end.size();
+    const int nif = (c->n_if_elems < c->ne) ? c->n_if_elems : 0, KI = c->hp_K;
+    for (int k = 0; k < KI; k++) {
+        c->hp_elem_begin.push_back(nif + (int)((long)(c->ne - nif) * k / KI));
+        c->hp_elem_end.push_back(nif + (int)((long)(c->ne - nif) * (k + 1) / KI));
+    }
+    if (nif > 0) { c->hp_elem_begin.push_back(0); c->hp_elem_end.push_back(nif); }
+    const int K = (int)c->hp_elem_end.size();
+    std::vector<int> last_chunk(nr, 0);
+    int run_max = 0;
+    auto each_fine = [&](const uint64_t m[2], auto &&fn) {
+        for (int w = 0; w < 2; w++)
+            for (uint64_t b = m[w]; b; b &= b - 1) fn(64 * w + __builtin_ctzll(b));
+    };
+    for (int k = 0; k < K; k++) {
+        uint64_t m[2] = {0, 0};
+        for (int e = c->hp_elem_begin[k]; e < c->hp_elem_end[k]; e++) { m[0] |= c->hp_elem_mask[(size_t)2 * e]; m[1] |= c->hp_elem_mask[(size_t)2 * e + 1]; }
+        each_fine(m, [&](int r) { const int j = std::min(r / fine_per, nr - 1); run_max = std::max(run_max, j); last_chunk[j] = k; });
+        c->hp_x_ranges_needed.push_back(run_max + 1);
+    }
+    // multi-GPU: ranges holding dofs shared with other ranks are final only after the halo-sum that follows the last chunk
+    // (group K); with local dofs numbered by global id these are the few ranges at both ends of a slab
+    each_fine(c->hp_shared_mask, [&](int r) { last_chunk[std::min(r / fine_per, nr - 1)] = K; });
+    c->hp_final.assign(K + 1, {});
+    for (int j = 0; j < nr; j++) c->hp_final[last_chunk[j]].push_back(j);
+    for (int j = 0; j < nr; j++)
+        c->hp_ess_end.push_back((int)(std::upper_bound(c->hp_ess_host.begin(), c->hp_ess_host.end(), c->hp_range_end[j] - 1) - c->hp_ess_host.begin()));
 }
 
 // How the halo-sum of an apply runs on this rank (P2PTail::mode): 0 = separate kernel(s) after the element kernel,
@@ -441,42 +489,24 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
                 gc[(size_t)e * DP3 + k] = em[g] ? ~g : g;
             }
         LPF_TRY(upload(c->gmap_c, gc.data(), gc.size(), &c->bytes));
-        // plan of the pipelined host entry point: K element chunks, R dof ranges; chunk k needs the first
-        // hp_x_ranges_needed[k] ranges of x, and range j of y is final after its last-touching chunk
+        // pipelined host entry point: remember which dof ranges every element touches, then build the plan (host_plan_build)
         const bool ess_sorted = std::is_sorted(d->ess, d->ess + c->ness);
         if (c->ndof >= (1 << 18) && c->ne >= 64 && ess_sorted) {
-            const int R = 32;
-            const int rs = ((c->ndof + R - 1) / R + 511) & ~511;              // range size, 4 KB aligned
-            for (int j = 0; j < R; j++) if ((long)j * rs < c->ndof) c->hp_range_end.push_back((int)std::min<long>((long)(j + 1) * rs, c->ndof));
-            const int nr = (int)c->hp_range_end.size();
-            // element chunks: the interior elements [n_if, ne) in 16 chunks (their dofs ascend with the element index, so
-            // chunk k only needs a prefix of x), then the interface block [0, n_if) -- it reads both ends of the slab and its
-            // rows are final only after the halo-sum anyway
-            const int nif = (c->n_if_elems < c->ne) ? c->n_if_elems : 0, KI = 16;
-            for (int k = 0; k < KI; k++) {
-                c->hp_elem_begin.push_back(nif + (int)((long)(c->ne - nif) * k / KI));
-                c->hp_elem_end.push_back(nif + (int)((long)(c->ne - nif) * (k + 1) / KI));
-            }
-            if (nif > 0) { c->hp_elem_begin.push_back(0); c->hp_elem_end.push_back(nif); }
-            const int K = (int)c->hp_elem_end.size();
-            std::vector<int> last_chunk(nr, 0);
-            int run_max = 0;
-            for (int k = 0; k < K; k++) {
-                for (int e = c->hp_elem_begin[k]; e < c->hp_elem_end[k]; e++)
-                    for (int q = 0; q < D3; q++) {
-                        const int g = d->gather[(size_t)e * D3 + q];
-                        run_max = std::max(run_max, g);
-                        last_chunk[g / rs] = k;
-                    }
-                c->hp_x_ranges_needed.push_back(run_max / rs + 1);
-            }
-            // multi-GPU: ranges holding dofs shared with other ranks are final only after the halo-sum that follows the
-            // last chunk (group K); with local dofs numbered by global id these are the few ranges at both ends of a slab
-            for (int i = 0; i < d->n_shared; i++) last_chunk[d->shared_dofs[i] / rs] = K;
-            c->hp_final.assign(K + 1, {});
-            for (int j = 0; j < nr; j++) c->hp_final[last_chunk[j]].push_back(j);
-            for (int j = 0; j < nr; j++)
-                c->hp_ess_end.push_back((int)(std::upper_bound(d->ess, d->ess + c->ness, c->hp_range_end[j] - 1) - d->ess));
+            c->hp_fine_rs = ((c->ndof + 127) / 128 + 511) & ~511;             // 128 fine ranges, 4 KB aligned
+            c->hp_elem_mask.assign((size_t)2 * c->ne, 0);
+            for (int e = 0; e < c->ne; e++)
+                for (int q = 0; q < D3; q++) {
+                    const int r = d->gather[(size_t)e * D3 + q] / c->hp_fine_rs;
+                    c->hp_elem_mask[(size_t)2 * e + (r >> 6)] |= 1ull << (r & 63);
+                }
+            for (int i = 0; i < d->n_shared; i++) { const int r = d->shared_dofs[i] / c->hp_fine_rs; c->hp_shared_mask[r >> 6] |= 1ull << (r & 63); }
+            c->hp_ess_host.assign(d->ess, d->ess + c->ness);
+            // granularity by vector size (profiles/r02_e2e_host_ab.txt: every copy costs ~4 us of DMA time on top of its bytes,
+            // every range of lag between H2D and D2H its transfer time): >= 2 MB per range
+            const size_t vbytes = sizeof(double) * (size_t)c->ndof;
+            c->hp_R = vbytes >= ((size_t)128 << 20) ? 64 : vbytes >= ((size_t)32 << 20) ? 32 : 16;
+            c->hp_K = c->hp_R >= 32 ? 16 : 8;
+            host_plan_build(c);
         }
         LPF_TRY(upload(c->essmask, em.data(), em.size(), &c->bytes));
         LPF_TRY(upload(c->ess, d->ess, (size_t)c->ness, &c->bytes));
@@ -700,6 +730,16 @@ int lpf_set_option(lpf_ctx *c, const char *name, long value)
     else if (k == "pdl") c->pdl = (int)value;
     else if (k == "affine") c->affine = (int)value;
     else if (k == "host_pipeline") c->host_pipeline = (int)value;
+    else if (k == "hp_ranges" || k == "hp_chunks") {      // granularity of the pipelined host entry point
+        const int v = (int)value;
+        if (k == "hp_ranges") { if (v != 16 && v != 32 && v != 64 && v != 128) { lpf::set_error("hp_ranges must be 16, 32, 64 or 128"); return LPF_ERR_ARG; } c->hp_R = v; }
+        else { if (v < 1 || v > 256) { lpf::set_error("hp_chunks must be in [1, 256]"); return LPF_ERR_ARG; } c->hp_K = v; }
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (auto e : c->hp_ev_x) cudaEventDestroy(e);
+        for (auto e : c->hp_ev_c) cudaEventDestroy(e);
+        c->hp_ev_x.clear(); c->hp_ev_c.clear();
+        host_plan_build(c);
+    }
     else if (k == "l2_persist") c->l2_persist = (int)value;
     else if (k == "verbose") c->verbose = (int)value;
     else if (k == "deterministic") { if (value) LPF_TRY(det_setup(c)); c->deterministic = value ? 1 : 0; }
@@ -836,11 +876,15 @@ static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
     if (!c->s_h2d) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-        c->hp_ev_x.resize(R); c->hp_ev_c.resize(K);
-        for (auto &e : c->hp_ev_x) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        for (auto &e : c->hp_ev_c) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->hp_ev_start, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->hp_ev_done, cudaEventDisableTiming));
+    }
+    if ((int)c->hp_ev_x.size() != R || (int)c->hp_ev_c.size() != K) {
+        for (auto e : c->hp_ev_x) cudaEventDestroy(e);
+        for (auto e : c->hp_ev_c) cudaEventDestroy(e);
+        c->hp_ev_x.assign(R, nullptr); c->hp_ev_c.assign(K, nullptr);
+        for (auto &e : c->hp_ev_x) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto &e : c->hp_ev_c) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     double *x = c->X, *y = c->tmp;
     // everything enqueued so far on the context stream (earlier users of X / tmp) precedes the copies

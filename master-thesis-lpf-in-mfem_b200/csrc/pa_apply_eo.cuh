@@ -59,18 +59,16 @@ __device__ __forceinline__ void eo_split(const double (&in)[N], double (&e)[(N +
 // EQ: early release of the q-data buffer.  The buffer is dead as soon as every thread has multiplied its column by the D
 // tensor -- before the backward z contraction, a third of the Z stage -- so the warps count themselves out on a shared-memory
 // counter and the LAST one issues the bulk copy of the next batch's q-data right there instead of behind the stage barrier:
-// the copy is in flight for a larger part of the batch (one q-data buffer per CTA is all that fits at orders 7, 8).
-template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false, bool OVL = false, int TABS = 0, int LAY = 0, int EQ = 0>
+// the copy is in flight for a larger part of the batch (one q-data buffer per CTA is all that fits at orders 7, 8).  Measured:
+// +1.5 % at order 7, -4...-10 % at orders 4, 8, 9 (the release point splits the Z stage's instruction schedule), so order 7 only.
+// Also measured and NOT adopted: dropping the fence.proxy.async in front of the refills (these buffers are only ever read by
+// the threads) -- 5-10 % slower at every order.
+template <int P, int E, bool DEN, int MINB, bool AFF = false, bool DET = false, bool OVL = false, int TABS = 0, int LAY = 0, bool EQ = false>
 __global__ void __launch_bounds__(ApplyCfg<P, E>::NT, MINB)
 pa_apply_eo_kernel(const ApplyKArgs ka)
 {
     using C = TmaCfg<P, E, AFF, LAY>;
-    constexpr bool EQR = (EQ & 1) && !AFF;
-    // EQ & 2: no fence.proxy.async before a refill.  The fence (SASS MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) orders generic-proxy
-    // WRITES before the async proxy; the q-data and gather-map buffers are only ever READ by the threads, and those reads are
-    // ordered before the refill by the barrier (or the release counter) the issuing thread has passed -- the same
-    // write-after-read hand-over as in any TMA load pipeline (consumer arrives on a barrier, producer issues the copy).
-    constexpr bool NOFENCE = (EQ & 2) != 0;
+    constexpr bool EQR = EQ && !AFF;
     constexpr int D = C::D, Q = C::Q, LX = C::LX, LY = C::LY, LZ = C::LZ;
     constexpr int DP3 = C::DP3, QE = C::QE, D3 = C::D3;
     const double *__restrict__ qd = ka.qd;
@@ -175,7 +173,7 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
         // gather map of the next batch (issued behind the first barrier after the previous batch's Xt stage, pa_apply_tma.cuh)
         if (tid == 0 && has_next) {
             const int n1 = batch_elems(bn);
-            if (!NOFENCE) fence_proxy_async();
+            fence_proxy_async();
             mbar_expect_tx(bar_i + nxt, (uint32_t)(n1 * DP3 * 4));
             bulk_g2s_stream(sidx + nxt * E * DP3, gmap + (size_t)bn * E * DP3, (uint32_t)(n1 * DP3 * 4), bar_i + nxt, l2pol);
         }
@@ -255,7 +253,7 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
                     *qcnt = 0;      // next increment: behind at least one CTA-wide barrier
                     if (has_next) {
                         const int n1 = batch_elems(bn);
-                        if (!NOFENCE) fence_proxy_async();
+                        fence_proxy_async();
                         mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
                         bulk_g2s_stream(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q, l2pol);
                     }
@@ -283,7 +281,7 @@ pa_apply_eo_kernel(const ApplyKArgs ka)
 
         if (!AFF && !EQR && tid == 0 && has_next) {
             const int n1 = batch_elems(bn);
-            if (!NOFENCE) fence_proxy_async();
+            fence_proxy_async();
             mbar_expect_tx(bar_q, (uint32_t)(n1 * QE * 8));
             bulk_g2s_stream(sq, qd + (size_t)bn * E * QE, (uint32_t)(n1 * QE * 8), bar_q, l2pol);
         }

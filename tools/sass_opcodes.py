@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "master-thesis-lpf-in-mfem_b200", "build")
 OPS = ["DFMA", "DADD", "DMUL", "DMMA", "LDCU", "LDC", "R2UR", "UBLKCP", "SYNCS", "REDG", "ATOMG", "LDS", "STS", "BAR", "LDL", "STL"]
 # (E, MINB) of the default stored-q-data kernel per order (apply_order.cu launch_default)
-DEFAULT = {1: (16, 3), 2: (8, 3), 3: (8, 2), 4: (3, 4), 5: (3, 2), 6: (2, 3), 7: (1, 3), 8: (1, 2), 9: (1, 1), 10: (1, 1)}
+DEFAULT = {1: (16, 3), 2: (8, 3), 3: (8, 2), 4: (3, 4), 5: (3, 2), 6: (2, 3), 7: (1, 4), 8: (1, 3), 9: (1, 2), 10: (1, 1)}
 
 
 def kernels(obj):
@@ -59,7 +59,7 @@ def main():
     ap.add_argument("--all", action="store_true")
     a = ap.parse_args()
     print("# SASS opcode counts of the PA apply kernels (static, per kernel; `python tools/sass_opcodes.py`)\n")
-    print("Template arguments: `pa_apply_eo_kernel<P, E, DEN, MINB, AFF, DET, OVL, TABS>`, `pa_apply_tma_kernel<P, E, DEN, MINB, DET, OVL>`.")
+    print("Template arguments: `pa_apply_eo_kernel<P, E, DEN, MINB, AFF, DET, OVL, TABS, LAY, EQ>`, `pa_apply_tma_kernel<P, E, DEN, MINB, DET, OVL>`.")
     print("The batch loop is fully unrolled, so the counts are (prologue/epilogue aside) the instructions one warp issues per batch of E elements.\n")
     print("| kernel | regs | stack | " + " | ".join(OPS) + " | total |")
     print("|---|---|---|" + "---|" * (len(OPS) + 1))
@@ -75,7 +75,8 @@ def main():
             name = re.sub(r"\(double const\*.*", "", name)
             E, MINB = DEFAULT[p]
             tabs, tabs_ovl = (1 if p >= 7 else 0), (1 if p >= 6 else 0)
-            pat = (rf"pa_apply_eo_kernel<{p}, {E}, (true|false), {MINB}, false, (true|false), (false, {tabs}|true, {tabs_ovl})>" if p >= 3
+            lay, eq = (1 if 7 <= p <= 9 else 0), ("true" if p == 7 else "false")      # apply_order.cu launch_default
+            pat = (rf"pa_apply_eo_kernel<{p}, {E}, (true|false), {MINB}, false, (true|false), (false, {tabs}|true, {tabs_ovl}), {lay}, {eq}>" if p >= 3
                    else rf"pa_apply_tma_kernel<{p}, {E}, (true|false), {MINB}, (true|false), (true|false)>")
             is_default = re.fullmatch(pat, name) is not None
             if not (a.all or is_default or "evec" in name):

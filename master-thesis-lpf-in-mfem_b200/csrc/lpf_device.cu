@@ -126,12 +126,12 @@ struct lpf_ctx {
     int sub_e0 = 0, sub_ne = -1;               // element sub-range for the next apply launch (-1 = all)
     int host_pipeline = 1;                     // option
     std::vector<int> hp_elem_begin, hp_elem_end; // [K] element range of chunk k
-    std::vector<int> hp_x_ranges_needed;       // [K] number of leading dof ranges chunk k reads
-    std::vector<std::vector<int>> hp_final;    // [K] dof ranges whose y is final once chunk k is done
-    std::vector<int> hp_range_end, hp_ess_end; // [R] end dof of range j, end position in the (sorted) ess list
+    std::vector<int> hp_x_end;                 // [K] chunk k reads x[0, hp_x_end[k]): ONE H2D copy per chunk brings the new part of the prefix
+    struct HpRun { int a, b, ea, eb; };        // dofs [a, b) of y, positions [ea, eb) of the (sorted) ess list inside them
+    std::vector<std::vector<HpRun>> hp_final;  // [K + 1] runs of y that are final once chunk k is done (K: after the halo-sum): one D2H copy each
     // what the plan is built from (kept so that options hp_ranges / hp_chunks can rebuild it): which of 128 fine dof
     // ranges every element touches (2 x 64-bit mask per element), the fine ranges holding shared dofs, the sorted ess list
-    int hp_R = 32, hp_K = 16, hp_fine_rs = 0;
+    int hp_R = 128, hp_K = 8, hp_fine_rs = 0;
     std::vector<uint64_t> hp_elem_mask;
     uint64_t hp_shared_mask[2] = {0, 0};
     std::vector<int> hp_ess_host;
@@ -195,21 +195,24 @@ int apply_full(lpf_ctx *c, bool constrained, const double *x, double *y, double 
     return apply_launch(c, gm, x, y, den, status);
 }
 
-// Plan of the pipelined host entry point (lpf_apply_T_host): R dof ranges (R in {16, 32, 64, 128}) and K element chunks.  The
-// interior elements [n_if, ne) go first in K chunks (their dofs ascend with the element index, so chunk k only needs a
-// prefix of x), then the interface block [0, n_if) -- it reads both ends of the slab and its rows are final only after the
-// halo-sum anyway.  Chunk k needs the first hp_x_ranges_needed[k] ranges of x; range j of y is final after its
-// last-touching chunk (group K: after the halo-sum).
+// Plan of the pipelined host entry point (lpf_apply_T_host).  Dependencies are tracked on hp_R dof ranges (128 fine ranges by
+// default), but copies are issued per element chunk: the interior elements [n_if, ne) go first in hp_K chunks (their dofs ascend
+// with the element index, so chunk k needs a prefix x[0, hp_x_end[k]) and ONE H2D copy brings what chunk k - 1 did not need
+// yet), then the interface block [0, n_if) -- it reads both ends of the slab and its rows are final only after the halo-sum.
+// The ranges of y whose last-touching chunk is k leave as merged contiguous runs (one or two D2H copies per chunk; group K:
+// after the halo-sum).  Every copy costs ~4 us of DMA time on top of its bytes (profiles/r02_e2e_host_ab.txt), so the number of
+// copies follows the number of chunks, not the resolution of the dependency tracking.
 void host_plan_build(lpf_ctx *c)
 {
-    c->hp_elem_begin.clear(); c->hp_elem_end.clear(); c->hp_x_ranges_needed.clear(); c->hp_final.clear();
-    c->hp_range_end.clear(); c->hp_ess_end.clear();
+    c->hp_elem_begin.clear(); c->hp_elem_end.clear(); c->hp_x_end.clear(); c->hp_final.clear();
     if (c->hp_elem_mask.empty()) return;
-    const int fine_per = 128 / c->hp_R;                       // fine ranges per plan range
+    const int fine_per = 128 / c->hp_R;                       // fine ranges per tracked range
     const long rs = (long)c->hp_fine_rs * fine_per;
-    for (int j = 0; j < c->hp_R; j++) if (j * rs < c->ndof) c->hp_range_end.push_back((int)std::min<long>((j + 1) * rs, c->ndof));
-    const int nr = (int)c->hp_range_end.size();
+    std::vector<int> range_end;
+    for (int j = 0; j < c->hp_R; j++) if (j * rs < c->ndof) range_end.push_back((int)std::min<long>((j + 1) * rs, c->ndof));
+    const int nr = (int)range_end.size();
     const int nif = (c->n_if_elems < c->ne) ? c->n_if_elems : 0, KI = c->hp_K;
+    // (uniform chunks: sizes ramping up and down geometrically -- short H2D head, short D2H tail -- measured no faster)
     for (int k = 0; k < KI; k++) {
         c->hp_elem_begin.push_back(nif + (int)((long)(c->ne - nif) * k / KI));
         c->hp_elem_end.push_back(nif + (int)((long)(c->ne - nif) * (k + 1) / KI));
@@ -226,15 +229,25 @@ void host_plan_build(lpf_ctx *c)
         uint64_t m[2] = {0, 0};
         for (int e = c->hp_elem_begin[k]; e < c->hp_elem_end[k]; e++) { m[0] |= c->hp_elem_mask[(size_t)2 * e]; m[1] |= c->hp_elem_mask[(size_t)2 * e + 1]; }
         each_fine(m, [&](int r) { const int j = std::min(r / fine_per, nr - 1); run_max = std::max(run_max, j); last_chunk[j] = k; });
-        c->hp_x_ranges_needed.push_back(run_max + 1);
+        c->hp_x_end.push_back(range_end[run_max]);
     }
+    c->hp_x_end[K - 1] = c->ndof;          // whatever no element reads still has to arrive (essential rows copy x)
     // multi-GPU: ranges holding dofs shared with other ranks are final only after the halo-sum that follows the last chunk
     // (group K); with local dofs numbered by global id these are the few ranges at both ends of a slab
     each_fine(c->hp_shared_mask, [&](int r) { last_chunk[std::min(r / fine_per, nr - 1)] = K; });
     c->hp_final.assign(K + 1, {});
-    for (int j = 0; j < nr; j++) c->hp_final[last_chunk[j]].push_back(j);
-    for (int j = 0; j < nr; j++)
-        c->hp_ess_end.push_back((int)(std::upper_bound(c->hp_ess_host.begin(), c->hp_ess_host.end(), c->hp_range_end[j] - 1) - c->hp_ess_host.begin()));
+    const auto &ess = c->hp_ess_host;
+    for (int j = 0; j < nr; j++) {
+        auto &runs = c->hp_final[last_chunk[j]];
+        const int a = j ? range_end[j - 1] : 0, b = range_end[j];
+        if (!runs.empty() && runs.back().b == a) runs.back().b = b;
+        else runs.push_back({a, b, 0, 0});
+    }
+    for (auto &runs : c->hp_final)
+        for (auto &r : runs) {
+            r.ea = (int)(std::lower_bound(ess.begin(), ess.end(), r.a) - ess.begin());
+            r.eb = (int)(std::lower_bound(ess.begin(), ess.end(), r.b) - ess.begin());
+        }
 }
 
 // How the halo-sum of an apply runs on this rank (P2PTail::mode): 0 = separate kernel(s) after the element kernel,
@@ -501,11 +514,11 @@ int create_impl(lpf_ctx *c, const lpf_space_desc *d, int device, void *stream)
                 }
             for (int i = 0; i < d->n_shared; i++) { const int r = d->shared_dofs[i] / c->hp_fine_rs; c->hp_shared_mask[r >> 6] |= 1ull << (r & 63); }
             c->hp_ess_host.assign(d->ess, d->ess + c->ness);
-            // granularity by vector size (profiles/r02_e2e_host_ab.txt: every copy costs ~4 us of DMA time on top of its bytes,
-            // every range of lag between H2D and D2H its transfer time): >= 2 MB per range
+            // chunks by vector size (profiles/r02_e2e_host_ab.txt: 8 chunks are fastest at 139 MB, 4 at 18 MB; every additional
+            // chunk costs ~13 us); dependencies tracked on all 128 fine ranges
             const size_t vbytes = sizeof(double) * (size_t)c->ndof;
-            c->hp_R = vbytes >= ((size_t)128 << 20) ? 64 : vbytes >= ((size_t)32 << 20) ? 32 : 16;
-            c->hp_K = c->hp_R >= 32 ? 16 : 8;
+            c->hp_R = 128;
+            c->hp_K = vbytes >= ((size_t)64 << 20) ? 8 : 4;
             host_plan_build(c);
         }
         LPF_TRY(upload(c->essmask, em.data(), em.size(), &c->bytes));
@@ -872,17 +885,17 @@ int lpf_apply_T(lpf_ctx *c, const double *x, double *y)
 // done -- PCIe is full duplex, so the call costs about ONE transfer instead of H2D + apply + D2H back to back.
 static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
 {
-    const int K = (int)c->hp_elem_end.size(), R = (int)c->hp_range_end.size();
+    const int K = (int)c->hp_elem_end.size();
     if (!c->s_h2d) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&c->hp_ev_start, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&c->hp_ev_done, cudaEventDisableTiming));
     }
-    if ((int)c->hp_ev_x.size() != R || (int)c->hp_ev_c.size() != K) {
+    if ((int)c->hp_ev_x.size() != K) {
         for (auto e : c->hp_ev_x) cudaEventDestroy(e);
         for (auto e : c->hp_ev_c) cudaEventDestroy(e);
-        c->hp_ev_x.assign(R, nullptr); c->hp_ev_c.assign(K, nullptr);
+        c->hp_ev_x.assign(K, nullptr); c->hp_ev_c.assign(K, nullptr);
         for (auto &e : c->hp_ev_x) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto &e : c->hp_ev_c) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
@@ -891,52 +904,58 @@ static int apply_T_host_pipelined(lpf_ctx *c, const double *xh, double *yh)
     CUDA_TRY(cudaEventRecord(c->hp_ev_start, c->stream));
     CUDA_TRY(cudaStreamWaitEvent(c->s_h2d, c->hp_ev_start, 0));
     CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->hp_ev_start, 0));
-    for (int j = 0; j < R; j++) {
-        const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
-        CUDA_TRY(cudaMemcpyAsync(x + a, xh + a, sizeof(double) * (b - a), cudaMemcpyHostToDevice, c->s_h2d));
-        CUDA_TRY(cudaEventRecord(c->hp_ev_x[j], c->s_h2d));
+    for (int k = 0, a = 0; k < K; k++) {                 // x: one copy per chunk, the part of its prefix that is new
+        const int b = std::max(a, c->hp_x_end[k]);
+        if (b > a) CUDA_TRY(cudaMemcpyAsync(x + a, xh + a, sizeof(double) * (b - a), cudaMemcpyHostToDevice, c->s_h2d));
+        CUDA_TRY(cudaEventRecord(c->hp_ev_x[k], c->s_h2d));
+        a = b;
     }
     CUDA_TRY(cudaMemsetAsync(y, 0, sizeof(double) * c->ndof, c->stream));
-    int waited = 0, rc = LPF_OK;
+    int waited = 0, rc = LPF_OK;                         // the context stream has waited for the x pieces [0, waited)
+    auto x_landed = [&](int dof_end) {                   // ... extend that to cover x[0, dof_end)
+        while (waited < K && (waited == 0 || c->hp_x_end[waited - 1] < dof_end)) {
+            const cudaError_t e = cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0);
+            if (e != cudaSuccess) return e;
+            waited++;
+        }
+        return cudaSuccess;
+    };
+    auto ess_rows = [&](const std::vector<lpf_ctx::HpRun> &runs) {      // essential rows of runs that are final now: y = x there
+        for (const auto &r : runs) {
+            if (r.eb <= r.ea) continue;
+            const cudaError_t e = x_landed(r.b);
+            if (e != cudaSuccess) return e;
+            copy_at_kernel<<<(r.eb - r.ea + 255) / 256, 256, 0, c->stream>>>(r.eb - r.ea, c->ess + r.ea, x, y);
+            c->launches++;
+        }
+        return cudaSuccess;
+    };
+    auto send_runs = [&](const std::vector<lpf_ctx::HpRun> &runs) {
+        for (const auto &r : runs) {
+            const cudaError_t e = cudaMemcpyAsync(yh + r.a, y + r.a, sizeof(double) * (r.b - r.a), cudaMemcpyDeviceToHost, c->s_d2h);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
     for (int k = 0; k < K && rc == LPF_OK; k++) {
-        for (; waited < c->hp_x_ranges_needed[k]; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
+        CUDA_TRY(x_landed(c->hp_x_end[k]));
         c->sub_e0 = c->hp_elem_begin[k];
         c->sub_ne = c->hp_elem_end[k] - c->sub_e0;
         rc = apply_launch(c, c->gmap_c, x, y, nullptr, nullptr);
         c->sub_ne = -1;
         if (rc != LPF_OK) break;
         if (c->hp_final[k].empty()) continue;
-        for (int j : c->hp_final[k]) {               // essential rows of the ranges that are final now: y = x there
-            const int ea = j ? c->hp_ess_end[j - 1] : 0, eb = c->hp_ess_end[j];
-            if (eb > ea) {
-                for (; waited <= j; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
-                copy_at_kernel<<<(eb - ea + 255) / 256, 256, 0, c->stream>>>(eb - ea, c->ess + ea, x, y);
-                c->launches++;
-            }
-        }
+        CUDA_TRY(ess_rows(c->hp_final[k]));
         CUDA_TRY(cudaEventRecord(c->hp_ev_c[k], c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->hp_ev_c[k], 0));
-        for (int j : c->hp_final[k]) {
-            const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
-            CUDA_TRY(cudaMemcpyAsync(yh + a, y + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, c->s_d2h));
-        }
+        CUDA_TRY(send_runs(c->hp_final[k]));
     }
-    if (rc == LPF_OK && !c->hp_final[K].empty()) {   // multi-GPU: halo-sum, then the ranges that hold shared dofs
+    if (rc == LPF_OK && !c->hp_final[K].empty()) {   // multi-GPU: halo-sum, then the runs that hold shared dofs
         rc = halo_sum(c, c->halo, y);
-        for (int j : c->hp_final[K]) {
-            const int ea = j ? c->hp_ess_end[j - 1] : 0, eb = c->hp_ess_end[j];
-            if (eb > ea && rc == LPF_OK) {
-                for (; waited <= j; waited++) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->hp_ev_x[waited], 0));
-                copy_at_kernel<<<(eb - ea + 255) / 256, 256, 0, c->stream>>>(eb - ea, c->ess + ea, x, y);
-                c->launches++;
-            }
-        }
+        if (rc == LPF_OK) CUDA_TRY(ess_rows(c->hp_final[K]));
         CUDA_TRY(cudaEventRecord(c->hp_ev_done, c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->s_d2h, c->hp_ev_done, 0));
-        for (int j : c->hp_final[K]) {
-            const int a = j ? c->hp_range_end[j - 1] : 0, b = c->hp_range_end[j];
-            CUDA_TRY(cudaMemcpyAsync(yh + a, y + a, sizeof(double) * (b - a), cudaMemcpyDeviceToHost, c->s_d2h));
-        }
+        CUDA_TRY(send_runs(c->hp_final[K]));
     } else if (rc == LPF_OK && c->nranks > 1) {
         rc = halo_sum(c, c->halo, y);                // a rank without shared dofs still takes part in the exchange
     }

@@ -1,5 +1,6 @@
-"""A/B of the pipelined host-buffer apply (lpf_apply_T_host, bench.py `e2e`): granularity of the plan (dof ranges x element
-chunks) against the un-pipelined H2D -> apply -> D2H sequence and the PCIe ceiling (tools/microbench/pcie_bw.py).
+"""A/B of the pipelined host-buffer apply (lpf_apply_T_host, bench.py `e2e`): number of element chunks (= copies per direction)
+and resolution of the dependency tracking, against the un-pipelined H2D -> apply -> D2H sequence and the PCIe ceiling
+(tools/microbench/pcie_bw.py).
     python tools/e2e_host_ab.py [--refine 2] [--order 4]
 """
 import argparse
@@ -47,10 +48,9 @@ def main():
     ctx.set_option("host_pipeline", 0)
     run("un-pipelined")
     ctx.set_option("host_pipeline", 1)
-    for R, K in [(32, 16), (16, 8), (32, 32), (64, 16), (64, 32), (64, 64), (128, 32), (128, 64), (128, 128)]:
-        ctx.set_option("hp_ranges", R)
+    for K in (2, 4, 6, 8, 12, 16, 32, 64):
         ctx.set_option("hp_chunks", K)
-        run(f"pipelined, {R} ranges x {K} chunks")
+        run(f"pipelined, {K} chunks")
     ctx.close()
 
 

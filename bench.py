@@ -338,7 +338,11 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(p, sp.ne), "peak_source": peak_src, "algorithmic_bytes_per_launch": ab,
                      "kernel_ms": ms_kernel, "kernel_ms_per_rank": {"min": min(kernel_ranks), "median": float(np.median(kernel_ranks)), "max": max(kernel_ranks)},
-                     "kernel": "pa_apply_eo_kernel" if p >= 3 else "pa_apply_tma_kernel"},
+                     "kernel": "pa_apply_eo_kernel" if p >= 3 else "pa_apply_tma_kernel",
+                     # the whole constrained apply behind `value` (zeroing of y + element kernel + essential rows): its own
+                     # bytes are the kernel's plus one 8-byte write per dof for the zeroing the scatter-add needs
+                     "whole_apply": {"bytes_per_step": ab + 8 * n, "ms": ms_max / a.steps,
+                                     "achieved": (ab + 8 * n) / (ms_max / a.steps) / 1e6, "frac": (ab + 8 * n) / (ms_max / a.steps) / 1e6 / peak}},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n * world, "d2h_bytes_per_step": 8 * n * world,
                 "steps": e2e_steps, "api": "lpf_apply_T_host (pinned host x -> device -> apply -> host y)"},
         "gpu_launches": int(launches),

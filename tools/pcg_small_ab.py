@@ -32,3 +32,5 @@ for _ in range(3):
 e1.record(); torch.cuda.synchronize()
 its = sum(i.iterations for i in ctx.last_solve_info())
 print(f"{os.path.basename(os.path.abspath(root)):8s} r={refine} {' '.join(sys.argv[3:]):28s} {e0.elapsed_time(e1) / 3:9.3f} ms per RK4 step, {1e3 * e0.elapsed_time(e1) / 3 / its:7.2f} us per CG iteration ({its} its)")
+ctx.close()
+del ctx, sp

@@ -259,7 +259,8 @@ long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launche
  *   "deterministic" [0]   1 = bit-reproducible results: the restriction-transpose is an ordered gather (element order, as
  *                         MFEM's CPU ElementRestriction::MultTranspose) of an E-vector instead of red.global.add, the
  *                         diagonal likewise; CG iteration counts are then identical from run to run.  ~20 % slower apply.
- *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30 = an alternative (E, CTAs/SM) pair;
+ *   "apply_variant" [0]   0 = tuned kernel per order; 20 = plain contractions; 30 = an alternative (E, CTAs/SM) pair; 40 / 41 = stage
+ *                         buffers aliased into each other (/ + early q-data release) at orders 5-9 (the default at orders 7-9);
  *                         33 = the round-1 kernels of orders 7 / 8 (kept as evidence for profiles/r02_sweep_orders.txt)
  *   "affine" [1]          affine fast path when every element is affine (lpf_affine_active)
  *   "use_graph" [1], "pcg_chunk" [16]   CUDA graph of pcg_chunk CG iterations, status polled once per chunk
@@ -269,6 +270,8 @@ long lpf_launch_count(lpf_ctx *ctx);                          /* kernels launche
  *                         the interface has <= "p2p_fuse_max" [2048] entries), 2 = inside the apply kernel, overlapped with the
  *                         interior elements
  *   "host_pipeline" [1]   lpf_apply_T_host overlaps H2D / element chunks / D2H
+ *   "hp_chunks" [8 from 64 MB per vector, else 4]   element chunks of that pipeline = copies per direction;
+ *   "hp_ranges" [128]     dof ranges its dependencies are tracked on (16, 32, 64 or 128)
  *   "l2_persist" [0]      persisting-L2 window over z, d, A d
  *   "max_ctas" [0 = resident CTAs x SMs]   caps the persistent grid (tests)
  *   "verbose" [0]         print the launch geometry of every apply kernel once

@@ -226,7 +226,7 @@ class Mesh:
                 _np(lib.lpf_mesh_bdr_attr(self.h), nb, np.int32))
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:      # lib is None while the interpreter shuts down
             lib.lpf_mesh_destroy(self.h)
             self.h = None
 
@@ -353,7 +353,7 @@ class Space:
         return xyz
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.lpf_space_destroy(self.h)
             self.h = None
 
@@ -517,7 +517,7 @@ class Context:
         return lib.lpf_device_bytes(self.h)
 
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:
             lib.lpf_destroy(self.h)
             self.h = None
 

@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-rk4", action="store_true", help="skip the PCG-per-RK-step measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rk4-refine", type=int, default=1)
+    ap.add_argument("--no-sustained", action="store_true", help="skip the burst-vs-sustained leg (about 1 s of back-to-back applies)")
     ap.add_argument("--opt", action="append", default=[], help="extra lpf_set_option name=value (tuning A/B), repeatable")
     ap.add_argument("--p2p-fuse", type=int, default=-1, help="N>1: option p2p_fuse (-1 = library default: halo exchange inside the apply kernel, overlapped)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="N>1: own NVLink peer-memory exchange or NCCL send/recv + all-reduce")
@@ -309,6 +310,26 @@ def run_ours(a):
             m = rk4_measure(lpf, torch, a, local, stream, world, rank, dist if world > 1 else None, weak=False, refine=r, affine_leg=False)
             strong[name] = {k: m[k] for k in ("workload", "ms_per_rk4_step", "ms_per_cg_iteration", "cg_iterations_per_stage", "gpu_launches_per_step")}
 
+    # burst vs sustained (profiles/r02_sustained.txt): everything above is timed within milliseconds of an idle period; after ~1 s of
+    # back-to-back applies the board sits at its power limit and the same kernel runs at lower SM clocks.  Reported next to the burst
+    # figure, never instead of it (the copy bandwidth the roofline divides by is a burst figure too, and flat under load).
+    sustained = None
+    if not a.no_sustained:
+        n_heat = max(a.steps, int(0.5 / max(ms_max / a.steps * 1e-3, 1e-6)))      # the same count on every rank: the exchange is collective
+        s2 = ClockSampler(local) if rank == 0 else None
+        if s2 is not None:
+            s2.start()
+        ctx.time_apply(x, y, n_heat)                  # n_heat whole applies + n_heat kernels: about one second
+        _, ms_ks, _ = ctx.time_apply(x, y, a.steps)
+        if s2 is not None:
+            s2.stop_flag = True
+            s2.join(timeout=2)
+        tks = torch.tensor([ms_ks], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tks, op=dist.ReduceOp.MAX)
+        sustained = {"kernel_ms": float(tks[0]) / a.steps, "after": "%d back-to-back applies + %d element kernels (about 1 s)" % (n_heat, n_heat),
+                     "clocks": s2.summary() if s2 is not None else None}
+
     # multi-GPU correctness carried by the bench line itself: a small tank solved on N ranks against the single-rank run
     parity = None
     if world > 1:
@@ -348,6 +369,10 @@ def run_ours(a):
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
+    if sustained is not None:
+        sustained["achieved"] = ab / (sustained["kernel_ms"] * 1e-3) / 1e9
+        sustained["frac"] = sustained["achieved"] / peak
+        line["roofline"]["sustained"] = sustained
     if aff is not None:
         line["affine_fastpath"] = aff
     if rk is not None:

@@ -47,10 +47,15 @@ class CpuTank:
         return self._dinv
 
     # ---- operator ----
-    def time_applies(self, steps, warmup):
-        """`steps` timed operator applies after `warmup` untimed ones (work buffers allocated once, as in MFEM)"""
+    def time_applies(self, steps, warmup, min_warm_s=0.5):
+        """`steps` timed operator applies after `warmup` untimed ones (work buffers allocated once, as in MFEM).  The warm-up
+        also lasts at least `min_warm_s` seconds: the OpenMP team and the host's clocks need a few hundred milliseconds of load
+        to reach their steady state (seen as a 10x slower first call on small tanks), and the baseline is quoted at that state."""
         x = np.random.default_rng(0).random(self.ndof) - 0.5
         self.cop.mult_n(x, max(1, warmup))
+        t_w = time.perf_counter()
+        while time.perf_counter() - t_w < min_warm_s:
+            self.cop.mult_n(x, 1)
         t0 = time.perf_counter()
         self.cop.mult_n(x, steps)
         return (time.perf_counter() - t0) / steps
